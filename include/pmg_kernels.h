@@ -1,0 +1,89 @@
+/*
+ * pmg_kernels.h -- thin C-ABI between the C host layer (portable-multigrid_b200/host)
+ * and the hand-written sm_100a CUDA kernels (portable-multigrid_b200/csrc).
+ *
+ * Plain pointers and sizes only; every function enqueues work on `stream`
+ * (a cudaStream_t passed as void*) and returns 0 or a negative pmg error code.
+ * Device pointers unless stated otherwise.  No CPU fallback exists behind any entry.
+ */
+#ifndef PMG_KERNELS_H
+#define PMG_KERNELS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMGK_MAX_N1 10
+
+/* One multigrid level as the kernels see it (structured box, lexicographic dofs). */
+typedef struct pmgk_level {
+  int degree;
+  int nx, ny, nz;        /* global cells */
+  int Nx, Ny, Nz;        /* global dofs per direction */
+  unsigned faces;        /* Dirichlet faces bitmask */
+  int z0, nzl;           /* local plane l holds global plane z0 + l */
+  int cz_lo, cz_hi;      /* owned cell layers */
+  int z_own_lo, z_own_hi;/* owned dof planes */
+  double h[3];
+  double S[PMGK_MAX_N1 * PMGK_MAX_N1]; /* nodal -> pencil eigenbasis, row a, column i (n1 x n1) */
+  double lam[PMGK_MAX_N1];
+  const double *dinv_tab;  /* device, (p+2)^3 */
+  const double *dinv_vec;  /* device, local vector or NULL */
+  int tile_variant;        /* tuning knob: 0 = default tile */
+} pmgk_level;
+
+enum { PMGK_APPLY = 0, PMGK_RESIDUAL = 1, PMGK_CHEB_FIRST = 2, PMGK_CHEB_STEP = 3 };
+
+/* K1 fused: out = epilogue(A u); replaces LaplaceOperator::vmult (+ smoother update)
+   (reference include/operators/portable_laplace_operator.h:557-719) */
+int pmgk_apply(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+               double *out, double f1, double f2, void *stream);
+/* number of kernel launches pmgk_apply issues (1) and the launch geometry it would use */
+int pmgk_apply_geometry(const pmgk_level *lv, int *grid, int *block, int *smem_bytes, int *n_chunks);
+
+/* inverse diagonal as an explicit vector (LaplaceOperator::compute_diagonal, :752-917) */
+int pmgk_fill_dinv(const pmgk_level *lv, double *dinv, void *stream);
+/* out = f * Dinv * b (first Chebyshev step from a zero guess) */
+int pmgk_scale_dinv(const pmgk_level *lv, double f, const double *b, double *out, void *stream);
+
+/* BLAS-1 on local vectors (LinearAlgebra::distributed::Vector ops used on the path) */
+int pmgk_set(double *x, double a, int64_t n, void *stream);
+int pmgk_copy(double *dst, const double *src, int64_t n, void *stream);
+int pmgk_axpby(double *out, double a, const double *x, double b, const double *y, int64_t n, void *stream); /* out = a x + b y */
+int pmgk_scale(double *x, double a, int64_t n, void *stream);
+/* result[0] = sum x_i y_i over [0,n): deterministic two-stage reduction; work >= pmgk_dot_work_doubles() */
+int pmgk_dot(const double *x, const double *y, int64_t n, double *result, double *work, void *stream);
+int pmgk_sum(const double *x, int64_t n, double *result, double *work, void *stream);
+int pmgk_dot_work_doubles(void);
+/* CG fused updates: x += alpha p, r -= alpha Ap, result[0] = r.r  (alpha read from device) */
+int pmgk_cg_update_xr(double *x, double *r, const double *p, const double *Ap, const double *alpha_dev,
+                      int64_t n, double *result, double *work, void *stream);
+/* p = z + beta p (beta read from device) */
+int pmgk_cg_update_p(double *p, const double *z, const double *beta_dev, int64_t n, void *stream);
+/* tiny device-scalar helper: out[0] = num[0] / den[0] */
+int pmgk_scalar_div(double *out, const double *num, const double *den, void *stream);
+/* x_i = ((first_global + i) mod 11), Chebyshev eigenvalue-estimate start vector */
+int pmgk_set_mod11(double *x, int64_t first_global, int64_t n, void *stream);
+
+/* transfers (K4-K7).  kind 0 = geometric (fine mesh = coarse refined once, same degree),
+   kind 1 = polynomial (same mesh, degree pc < pf).  P1d: device, (pc+1) x nf1 row-major,
+   nf1 = 2p+1 (h) or pf+1 (p).  scratch: device doubles, >= pmgk_restrict_scratch_doubles(). */
+int pmgk_prolongate_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
+                            double *dst_fine, const double *src_coarse, void *stream);
+int pmgk_restrict_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
+                          double *dst_coarse, const double *src_fine, double *scratch, void *stream);
+int64_t pmgk_restrict_scratch_doubles(int kind, const pmgk_level *coarse, const pmgk_level *fine);
+
+/* device properties the host layer needs */
+int pmgk_device_sm_count(void);
+/* FP64 microbenchmarks (roofline denominators): returns TFLOP/s */
+int pmgk_bench_fp64_fma(double *tflops, void *stream);
+int pmgk_bench_fp64_dmma(double *tflops, void *stream);
+int pmgk_bench_hbm_copy(double *gbs, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

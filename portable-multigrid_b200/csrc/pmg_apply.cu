@@ -1,0 +1,121 @@
+// pmg_apply.cu -- CUDA kernel + thin C-ABI launcher for the fused Laplace apply (K1).
+// Algorithm and citations: pmg_apply_tile.h.  sm_100a only; there is no fallback path.
+#include "pmg_apply_tile.h"
+#include "pmg_cuda_common.h"
+#include "pmg_kernels.h"
+
+template <class Tile>
+struct PmgDeviceExec {
+  typename Tile::ThreadState st;
+  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+template <int P, int BX, int BY>
+__global__ void __launch_bounds__(PmgApplyTile<P, BX, BY>::NT, 1)
+pmg_apply_kernel(const __grid_constant__ PmgApplyParams<P> p)
+{
+  using Tile = PmgApplyTile<P, BX, BY>;
+  extern __shared__ double pmg_smem[];
+  PmgDeviceExec<Tile> ex;
+  const int b = blockIdx.x;
+  const int tile_x = b % p.tiles_x;
+  const int tile_y = (b / p.tiles_x) % p.tiles_y;
+  const int chunk = b / (p.tiles_x * p.tiles_y);
+  Tile::run(p, ex, pmg_smem, tile_x, tile_y, chunk);
+}
+
+// choose the number of z-chunks: minimise waves * (layers + halo layer)
+static void choose_chunks(int tiles, int layers, int slots, int *n_chunks, int *layers_per_chunk)
+{
+  long best_cost = -1;
+  int best_c = 1;
+  for (int c = 1; c <= layers; ++c) {
+    const int lpc = (layers + c - 1) / c;
+    const int used = (layers + lpc - 1) / lpc;
+    if (used != c) continue;
+    const long waves = ((long)tiles * c + slots - 1) / slots;
+    const long cost = waves * (lpc + (c > 1 ? 1 : 0));
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+  }
+  *n_chunks = best_c;
+  *layers_per_chunk = (layers + best_c - 1) / best_c;
+}
+
+template <int P, int BX, int BY>
+static int launch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                  double *out, double f1, double f2, cudaStream_t stream, int *geom)
+{
+  using Tile = PmgApplyTile<P, BX, BY>;
+  constexpr int N1 = P + 1;
+  PmgApplyParams<P> p;
+  p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
+  p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
+  p.faces = lv->faces;
+  p.z0 = lv->z0; p.nzl = lv->nzl;
+  p.cz_lo = lv->cz_lo; p.cz_hi = lv->cz_hi;
+  p.z_own_lo = lv->z_own_lo; p.z_own_hi = lv->z_own_hi;
+  p.tiles_x = (lv->nx + BX - 1) / BX;
+  p.tiles_y = (lv->ny + BY - 1) / BY;
+  const int smem_bytes = Tile::SMEM_DOUBLES * (int)sizeof(double);
+  static int configured = 0;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_apply_kernel<P, BX, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_apply_kernel<P, BX, BY>, Tile::NT, smem_bytes));
+    if (ctas_per_sm < 1) return PMG_ERR_CUDA;
+    configured = 1;
+  }
+  const int slots = pmgk_device_sm_count() * ctas_per_sm;
+  choose_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, &p.n_chunks, &p.layers_per_chunk);
+  for (int i = 0; i < N1 * N1; ++i) p.S[i] = lv->S[i];
+  for (int i = 0; i < N1; ++i) p.lam[i] = lv->lam[i];
+  p.c[0] = lv->h[1] * lv->h[2] / lv->h[0];
+  p.c[1] = lv->h[0] * lv->h[2] / lv->h[1];
+  p.c[2] = lv->h[0] * lv->h[1] / lv->h[2];
+  p.mode = mode; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
+  p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
+  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  if (geom) { geom[0] = grid; geom[1] = Tile::NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
+  pmg_apply_kernel<P, BX, BY><<<grid, Tile::NT, smem_bytes, stream>>>(p);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+static int dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                    double *out, double f1, double f2, cudaStream_t s, int *geom)
+{
+  if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
+  switch (lv->degree) {
+    case 1: return launch<1, 16, 16>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 2: return launch<2, 12, 12>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 3: return launch<3, 10, 10>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 4: return launch<4, 8, 8>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 5: return launch<5, 7, 7>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 6: return launch<6, 6, 6>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 7: return launch<7, 5, 5>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 8: return launch<8, 4, 4>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    default: return PMG_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int pmgk_apply(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                          double *out, double f1, double f2, void *stream)
+{
+  if (!lv || !u || !out) return PMG_ERR_ARG;
+  if (mode != PMGK_APPLY && !b) return PMG_ERR_ARG;
+  if (u == out) return PMG_ERR_ARG; /* the halo of u is read by neighbouring tiles */
+  return dispatch(lv, mode, u, b, xold, out, f1, f2, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int pmgk_apply_geometry(const pmgk_level *lv, int *grid, int *block, int *smem_bytes, int *n_chunks)
+{
+  int g[4] = {0, 0, 0, 0};
+  const int rc = dispatch(lv, 0, (const double *)8, nullptr, nullptr, (double *)16, 0, 0, 0, g);
+  if (grid) *grid = g[0];
+  if (block) *block = g[1];
+  if (smem_bytes) *smem_bytes = g[2];
+  if (n_chunks) *n_chunks = g[3];
+  return rc;
+}

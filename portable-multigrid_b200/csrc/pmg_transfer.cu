@@ -1,0 +1,375 @@
+// pmg_transfer.cu -- h- and p-multigrid transfer kernels (K4-K7) and inverse-diagonal kernels (K2/K3).
+//
+// Replaces, on the structured box mesh,
+//   h_mg_transfer::CellProlongationKernel / CellRestrictionKernel
+//     (reference include/multigrid/portable_geometric_transfer.h:150-387, 450-684) and
+//   p_mg_transfer::CellProlongationKernel / CellRestrictionKernel
+//     (reference include/multigrid/portable_polynomial_tranfer.h:103-326, 390-615).
+// Same tensor algebra (three 1-D contractions with the (pc+1) x nf1 matrix), different data
+// movement: indices, weights and masks are computed from the cell position instead of being
+// streamed (the reference reads a u32 index and an f64 weight per patch dof), and every fine
+// dof is handled by exactly one patch (low-side ownership) so neither atomics nor the weight
+// array are needed:  sum_patches w_f P (.) with w_f = 1/multiplicity  ==  P (.) taken once.
+// Restriction is two deterministic passes (cell-local contraction, then a gather per coarse dof).
+#include "pmg_cuda_common.h"
+#include "pmg_kernels.h"
+
+namespace {
+
+struct XferGeom {
+  int kind;            // 0 = h, 1 = p
+  int pc, pf;          // degrees
+  int NC, NF;          // 1-D sizes of the coarse cell / fine patch
+  int fstep;           // fine dof offset per coarse cell: 2p (h) or pf (p)
+  int ncx, ncy, ncz;   // coarse cells (global)
+  int Ncx, Ncy, Ncz;   // coarse dofs (global)
+  int Nfx, Nfy, Nfz;   // fine dofs (global)
+  unsigned faces;
+  // slabs
+  int c_z0, f_z0;      // first stored plane of the coarse / fine local vectors
+  int ccz_lo, ccz_hi;  // coarse cell layers handled by this rank
+  int c_zown_lo, c_zown_hi, f_zown_lo, f_zown_hi;
+  int c_nzl, f_nzl;
+};
+
+__device__ __forceinline__ bool on_dirichlet(int gx, int gy, int gz, int Nx, int Ny, int Nz, unsigned faces)
+{
+  return (gx == 0 && (faces & 1u)) || (gx == Nx - 1 && (faces >> 1 & 1u)) || (gy == 0 && (faces >> 2 & 1u)) ||
+         (gy == Ny - 1 && (faces >> 3 & 1u)) || (gz == 0 && (faces >> 4 & 1u)) || (gz == Nz - 1 && (faces >> 5 & 1u));
+}
+
+// one CTA handles CPB consecutive coarse cells (x fastest)
+template <int CPB>
+__global__ void __launch_bounds__(256) k_prolongate(const XferGeom g, const double *__restrict__ P1d, double *dst, const double *__restrict__ src)
+{
+  extern __shared__ double sm[];
+  const int NC = g.NC, NF = g.NF;
+  const int nvc = NC * NC * NC, nt1 = NC * NC * NF, nt2 = NC * NF * NF;
+  double *sP = sm;                       // NC*NF
+  double *vc = sP + NC * NF;             // CPB * nvc
+  double *t1 = vc + CPB * nvc;           // CPB * nt1
+  double *t2 = t1 + CPB * nt1;           // CPB * nt2
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
+  const int64_t cell0 = (int64_t)blockIdx.x * CPB;
+
+  for (int i = tid; i < NC * NF; i += nth) sP[i] = P1d[i];
+  // gather coarse cell values
+  for (int w = tid; w < CPB * nvc; w += nth) {
+    const int c = w / nvc, i = w % nvc;
+    const int64_t cell = cell0 + c;
+    double v = 0.0;
+    if (cell < ncells) {
+      const int cx = (int)(cell % g.ncx), cy = (int)((cell / g.ncx) % g.ncy), cz = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
+      const int ix = i % NC, iy = (i / NC) % NC, iz = i / (NC * NC);
+      const int gx = cx * g.pc + ix, gy = cy * g.pc + iy, gz = cz * g.pc + iz;
+      // h: constrained coarse dofs read as 0 (dof_indices_coarse == invalid, :170-173);
+      // p: read unmasked (:115-121)
+      if (g.kind == 1 || !on_dirichlet(gx, gy, gz, g.Ncx, g.Ncy, g.Ncz, g.faces))
+        v = src[((int64_t)(gz - g.c_z0) * g.Ncy + gy) * g.Ncx + gx];
+    }
+    vc[w] = v;
+  }
+  __syncthreads();
+  // x: t1[z][y][xf]
+  for (int w = tid; w < CPB * nt1; w += nth) {
+    const int c = w / nt1, r = w % nt1;
+    const int xf = r % NF, zy = r / NF;
+    const double *in = vc + c * nvc + zy * NC;
+    double s = 0.0;
+    for (int k = 0; k < NC; ++k) s += sP[k * NF + xf] * in[k];
+    t1[w] = s;
+  }
+  __syncthreads();
+  // y: t2[z][yf][xf]
+  for (int w = tid; w < CPB * nt2; w += nth) {
+    const int c = w / nt2, r = w % nt2;
+    const int xf = r % NF, yf = (r / NF) % NF, z = r / (NF * NF);
+    const double *in = t1 + c * nt1 + z * NC * NF + xf;
+    double s = 0.0;
+    for (int k = 0; k < NC; ++k) s += sP[k * NF + yf] * in[k * NF];
+    t2[w] = s;
+  }
+  __syncthreads();
+  // z + owner write: dst += value on owned, unconstrained fine dofs
+  const int nf3 = NF * NF * NF;
+  for (int w = tid; w < CPB * nf3; w += nth) {
+    const int c = w / nf3, r = w % nf3;
+    const int64_t cell = cell0 + c;
+    if (cell >= ncells) continue;
+    const int xf = r % NF, yf = (r / NF) % NF, zf = r / (NF * NF);
+    const int cx = (int)(cell % g.ncx), cy = (int)((cell / g.ncx) % g.ncy), cz = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
+    if ((xf == NF - 1 && cx != g.ncx - 1) || (yf == NF - 1 && cy != g.ncy - 1) || (zf == NF - 1 && cz != g.ncz - 1)) continue;
+    const int gx = cx * g.fstep + xf, gy = cy * g.fstep + yf, gz = cz * g.fstep + zf;
+    if (gz < g.f_zown_lo || gz >= g.f_zown_hi) continue;
+    if (on_dirichlet(gx, gy, gz, g.Nfx, g.Nfy, g.Nfz, g.faces)) continue; // weight 0 / masked (:1346-1349, p :306-324)
+    const double *in = t2 + c * nt2 + yf * NF + xf;
+    double s = 0.0;
+    for (int k = 0; k < NC; ++k) s += sP[k * NF + zf] * in[k * NF * NF];
+    dst[((int64_t)(gz - g.f_z0) * g.Nfy + gy) * g.Nfx + gx] += s;
+  }
+}
+
+// pass 1 of the restriction: cell-local (P^T x P^T x P^T) applied to the patch's owned fine dofs
+template <int CPB>
+__global__ void __launch_bounds__(256) k_restrict_cells(const XferGeom g, const double *__restrict__ P1d, double *scratch, const double *__restrict__ src)
+{
+  extern __shared__ double sm[];
+  const int NC = g.NC, NF = g.NF;
+  const int nf3 = NF * NF * NF, nt1 = NC * NF * NF, nt2 = NC * NC * NF, nvc = NC * NC * NC;
+  double *sP = sm;                 // NC*NF
+  double *vf = sP + NC * NF;       // CPB*nf3
+  double *t1 = vf + CPB * nf3;     // CPB*nt1   [zc][yf][xf]
+  double *t2 = t1 + CPB * nt1;     // CPB*nt2   [zc][yc][xf]
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
+  const int64_t cell0 = (int64_t)blockIdx.x * CPB;
+  for (int i = tid; i < NC * NF; i += nth) sP[i] = P1d[i];
+  for (int w = tid; w < CPB * nf3; w += nth) {
+    const int c = w / nf3, r = w % nf3;
+    const int64_t cell = cell0 + c;
+    double v = 0.0;
+    if (cell < ncells) {
+      const int xf = r % NF, yf = (r / NF) % NF, zf = r / (NF * NF);
+      const int cx = (int)(cell % g.ncx), cy = (int)((cell / g.ncx) % g.ncy), cz = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
+      const bool owned = !((xf == NF - 1 && cx != g.ncx - 1) || (yf == NF - 1 && cy != g.ncy - 1) || (zf == NF - 1 && cz != g.ncz - 1));
+      const int gx = cx * g.fstep + xf, gy = cy * g.fstep + yf, gz = cz * g.fstep + zf;
+      if (owned && !on_dirichlet(gx, gy, gz, g.Nfx, g.Nfy, g.Nfz, g.faces))
+        v = src[((int64_t)(gz - g.f_z0) * g.Nfy + gy) * g.Nfx + gx];
+    }
+    vf[w] = v;
+  }
+  __syncthreads();
+  // z: t1[zc][yf][xf] = sum_zf P[zc][zf] vf[zf][yf][xf]
+  for (int w = tid; w < CPB * nt1; w += nth) {
+    const int c = w / nt1, r = w % nt1;
+    const int xy = r % (NF * NF), zc = r / (NF * NF);
+    const double *in = vf + c * nf3 + xy;
+    double s = 0.0;
+    for (int k = 0; k < NF; ++k) s += sP[zc * NF + k] * in[k * NF * NF];
+    t1[w] = s;
+  }
+  __syncthreads();
+  // y: t2[zc][yc][xf]
+  for (int w = tid; w < CPB * nt2; w += nth) {
+    const int c = w / nt2, r = w % nt2;
+    const int xf = r % NF, yc = (r / NF) % NC, zc = r / (NF * NC);
+    const double *in = t1 + c * nt1 + zc * NF * NF + xf;
+    double s = 0.0;
+    for (int k = 0; k < NF; ++k) s += sP[yc * NF + k] * in[k * NF];
+    t2[w] = s;
+  }
+  __syncthreads();
+  // x: scratch[cell][zc][yc][xc]
+  for (int w = tid; w < CPB * nvc; w += nth) {
+    const int c = w / nvc, r = w % nvc;
+    const int64_t cell = cell0 + c;
+    if (cell >= ncells) continue;
+    const int xc = r % NC, zy = r / NC;
+    const double *in = t2 + c * nt2 + zy * NF;
+    double s = 0.0;
+    for (int k = 0; k < NF; ++k) s += sP[xc * NF + k] * in[k];
+    scratch[cell * nvc + r] = s;
+  }
+}
+
+// pass 2: every coarse dof of the handled layers gathers its <= 8 cell-local contributions
+__global__ void k_restrict_gather(const XferGeom g, double *dst, const double *__restrict__ scratch)
+{
+  const int NC = g.NC, p = g.pc;
+  const int nvc = NC * NC * NC;
+  const int z_lo = g.ccz_lo * p, z_hi = g.ccz_hi * p; // planes z_lo..z_hi inclusive receive contributions
+  const int64_t plane = (int64_t)g.Ncx * g.Ncy;
+  const int64_t total = plane * (z_hi - z_lo + 1);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int gx = (int)(idx % g.Ncx), gy = (int)((idx / g.Ncx) % g.Ncy), gz = z_lo + (int)(idx / plane);
+    if (gz - g.c_z0 < 0 || gz - g.c_z0 >= g.c_nzl) continue;
+    if (on_dirichlet(gx, gy, gz, g.Ncx, g.Ncy, g.Ncz, g.faces)) continue; // constrained coarse dofs are skipped (:674-682)
+    double s = 0.0;
+    for (int sz = 0; sz < 2; ++sz) {
+      int cz = gz / p, iz = gz % p;
+      if (sz == 1) { if (iz != 0) continue; cz -= 1; iz = p; }
+      if (cz < g.ccz_lo || cz >= g.ccz_hi) continue;
+      for (int sy = 0; sy < 2; ++sy) {
+        int cy = gy / p, iy = gy % p;
+        if (sy == 1) { if (iy != 0) continue; cy -= 1; iy = p; }
+        if (cy < 0 || cy >= g.ncy) continue;
+        for (int sx = 0; sx < 2; ++sx) {
+          int cx = gx / p, ix = gx % p;
+          if (sx == 1) { if (ix != 0) continue; cx -= 1; ix = p; }
+          if (cx < 0 || cx >= g.ncx) continue;
+          const int64_t cell = ((int64_t)(cz - g.ccz_lo) * g.ncy + cy) * g.ncx + cx;
+          s += scratch[cell * nvc + (iz * NC + iy) * NC + ix];
+        }
+      }
+    }
+    dst[(int64_t)(gz - g.c_z0) * plane + (int64_t)gy * g.Ncx + gx] += s;
+  }
+}
+
+int make_geom(int kind, const pmgk_level *c, const pmgk_level *f, XferGeom *g)
+{
+  g->kind = kind; g->pc = c->degree; g->pf = f->degree;
+  if (kind == 0) {
+    if (c->degree != f->degree || f->nx != 2 * c->nx || f->ny != 2 * c->ny || f->nz != 2 * c->nz) return PMG_ERR_ARG;
+    g->NC = c->degree + 1; g->NF = 2 * c->degree + 1; g->fstep = 2 * c->degree;
+    if (f->cz_lo != 2 * c->cz_lo || f->cz_hi != 2 * c->cz_hi) return PMG_ERR_ARG;
+  } else {
+    if (c->degree >= f->degree || f->nx != c->nx || f->ny != c->ny || f->nz != c->nz) return PMG_ERR_ARG;
+    g->NC = c->degree + 1; g->NF = f->degree + 1; g->fstep = f->degree;
+    if (f->cz_lo != c->cz_lo || f->cz_hi != c->cz_hi) return PMG_ERR_ARG;
+  }
+  if (c->faces != f->faces) return PMG_ERR_ARG;
+  g->ncx = c->nx; g->ncy = c->ny; g->ncz = c->nz;
+  g->Ncx = c->Nx; g->Ncy = c->Ny; g->Ncz = c->Nz;
+  g->Nfx = f->Nx; g->Nfy = f->Ny; g->Nfz = f->Nz;
+  g->faces = c->faces;
+  g->c_z0 = c->z0; g->f_z0 = f->z0; g->c_nzl = c->nzl; g->f_nzl = f->nzl;
+  g->ccz_lo = c->cz_lo; g->ccz_hi = c->cz_hi;
+  g->c_zown_lo = c->z_own_lo; g->c_zown_hi = c->z_own_hi;
+  g->f_zown_lo = f->z_own_lo; g->f_zown_hi = f->z_own_hi;
+  return 0;
+}
+
+int pick_cpb(int NC, int NF)
+{
+  const int per_cell = NF * NF * NF + NC * NF * NF + NC * NC * NF; // doubles of shared memory per cell (restriction)
+  int cpb = 1;
+  while (cpb < 8 && (cpb * 2) * per_cell * 8 <= 40 * 1024 && (cpb * NF * NF * NF) < 1024) cpb *= 2;
+  return cpb;
+}
+
+} // namespace
+
+extern "C" int64_t pmgk_restrict_scratch_doubles(int kind, const pmgk_level *coarse, const pmgk_level *fine)
+{
+  (void)kind; (void)fine;
+  const int NC = coarse->degree + 1;
+  return (int64_t)coarse->nx * coarse->ny * (coarse->cz_hi - coarse->cz_lo) * NC * NC * NC;
+}
+
+template <int CPB>
+static int launch_prolongate(const XferGeom &g, const double *P1d, double *dst, const double *src, cudaStream_t s)
+{
+  const int NC = g.NC, NF = g.NF;
+  const size_t smem = sizeof(double) * (NC * NF + CPB * (NC * NC * NC + NC * NC * NF + NC * NF * NF));
+  const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
+  if (smem > 48 * 1024) PMG_CUDA_CHECK(cudaFuncSetAttribute(k_prolongate<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_prolongate<CPB><<<(unsigned)((ncells + CPB - 1) / CPB), 256, smem, s>>>(g, P1d, dst, src);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+template <int CPB>
+static int launch_restrict(const XferGeom &g, const double *P1d, double *scratch, const double *src, cudaStream_t s)
+{
+  const int NC = g.NC, NF = g.NF;
+  const size_t smem = sizeof(double) * (NC * NF + CPB * (NF * NF * NF + NC * NF * NF + NC * NC * NF));
+  const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
+  if (smem > 48 * 1024) PMG_CUDA_CHECK(cudaFuncSetAttribute(k_restrict_cells<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_restrict_cells<CPB><<<(unsigned)((ncells + CPB - 1) / CPB), 256, smem, s>>>(g, P1d, scratch, src);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+extern "C" int pmgk_prolongate_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
+                                       double *dst_fine, const double *src_coarse, void *stream)
+{
+  XferGeom g;
+  const int rc = make_geom(kind, coarse, fine, &g);
+  if (rc) return rc;
+  if (g.ccz_hi <= g.ccz_lo) return 0;
+  switch (pick_cpb(g.NC, g.NF)) {
+    case 8: return launch_prolongate<8>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
+    case 4: return launch_prolongate<4>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
+    case 2: return launch_prolongate<2>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
+    default: return launch_prolongate<1>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
+  }
+}
+
+extern "C" int pmgk_restrict_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
+                                     double *dst_coarse, const double *src_fine, double *scratch, void *stream)
+{
+  XferGeom g;
+  int rc = make_geom(kind, coarse, fine, &g);
+  if (rc) return rc;
+  if (g.ccz_hi <= g.ccz_lo) return 0;
+  switch (pick_cpb(g.NC, g.NF)) {
+    case 8: rc = launch_restrict<8>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
+    case 4: rc = launch_restrict<4>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
+    case 2: rc = launch_restrict<2>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
+    default: rc = launch_restrict<1>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
+  }
+  if (rc) return rc;
+  const int64_t total = (int64_t)g.Ncx * g.Ncy * ((g.ccz_hi - g.ccz_lo) * g.pc + 1);
+  int64_t nb = (total + 255) / 256;
+  const int cap = pmgk_device_sm_count() * 8;
+  if (nb > cap) nb = cap;
+  k_restrict_gather<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(g, dst_coarse, scratch);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+// ---- inverse diagonal ------------------------------------------------------
+namespace {
+
+struct DiagGeom {
+  int P, Nx, Ny, Nz, z0, z_lo, z_hi;
+  unsigned faces;
+};
+
+__device__ __forceinline__ int pos_type(int g, int N, int P) { return (g == 0) ? P : (g == N - 1) ? P + 1 : g % P; }
+
+__global__ void k_dinv(const DiagGeom g, const double *__restrict__ tab, double f, const double *b, double *out)
+{
+  const int64_t plane = (int64_t)g.Nx * g.Ny;
+  const int64_t total = plane * (g.z_hi - g.z_lo);
+  const int T = g.P + 2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int gx = (int)(idx % g.Nx), gy = (int)((idx / g.Nx) % g.Ny), gz = g.z_lo + (int)(idx / plane);
+    const int64_t l = (int64_t)(gz - g.z0) * plane + (int64_t)gy * g.Nx + gx;
+    double d;
+    if (on_dirichlet(gx, gy, gz, g.Nx, g.Ny, g.Nz, g.faces)) d = 1.0;
+    else d = tab[pos_type(gx, g.Nx, g.P) + T * (pos_type(gy, g.Ny, g.P) + T * pos_type(gz, g.Nz, g.P))];
+    out[l] = b ? f * d * b[l] : d;
+  }
+}
+
+__global__ void k_dinv_vec(const double *__restrict__ dinv, double f, const double *__restrict__ b, double *out, int64_t n)
+{
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = f * dinv[i] * b[i];
+}
+
+int launch_dinv(const pmgk_level *lv, double f, const double *b, double *out, cudaStream_t s)
+{
+  DiagGeom g;
+  g.P = lv->degree; g.Nx = lv->Nx; g.Ny = lv->Ny; g.Nz = lv->Nz; g.z0 = lv->z0;
+  g.z_lo = lv->z0; g.z_hi = lv->z0 + lv->nzl; // all stored planes (ghost planes get consistent values)
+  g.faces = lv->faces;
+  const int64_t total = (int64_t)lv->Nx * lv->Ny * lv->nzl;
+  int64_t nb = (total + 255) / 256;
+  const int cap = pmgk_device_sm_count() * 8;
+  if (nb > cap) nb = cap;
+  if (nb < 1) return 0;
+  if (b && lv->dinv_vec) k_dinv_vec<<<(unsigned)nb, 256, 0, s>>>(lv->dinv_vec, f, b, out, total);
+  else k_dinv<<<(unsigned)nb, 256, 0, s>>>(g, lv->dinv_tab, f, b, out);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+} // namespace
+
+extern "C" int pmgk_fill_dinv(const pmgk_level *lv, double *dinv, void *stream)
+{
+  return launch_dinv(lv, 1.0, nullptr, dinv, (cudaStream_t)stream);
+}
+
+extern "C" int pmgk_scale_dinv(const pmgk_level *lv, double f, const double *b, double *out, void *stream)
+{
+  return launch_dinv(lv, f, b, out, (cudaStream_t)stream);
+}

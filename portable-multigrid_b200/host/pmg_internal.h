@@ -1,0 +1,130 @@
+/* pmg_internal.h -- internal declarations of the C host layer. */
+#ifndef PMG_INTERNAL_H
+#define PMG_INTERNAL_H
+
+#include <cuda_runtime_api.h>
+#include <nccl.h>
+#include <stdint.h>
+#include "pmg.h"
+#include "pmg_kernels.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void pmg_set_error(const char *fmt, ...);
+void pmg_count_launch(int n);
+
+#define PMG_CHECK(call)                        \
+  do {                                         \
+    int pmg_rc_ = (call);                      \
+    if (pmg_rc_ != PMG_OK) return pmg_rc_;     \
+  } while (0)
+
+#define PMG_CUDA(call)                                                                            \
+  do {                                                                                            \
+    cudaError_t pmg_e_ = (call);                                                                  \
+    if (pmg_e_ != cudaSuccess) {                                                                  \
+      pmg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(pmg_e_)); \
+      return PMG_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define PMG_NCCL(call)                                                                            \
+  do {                                                                                            \
+    ncclResult_t pmg_n_ = (call);                                                                 \
+    if (pmg_n_ != ncclSuccess) {                                                                  \
+      pmg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, ncclGetErrorString(pmg_n_)); \
+      return PMG_ERR_NCCL;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+/* pmg_fe.c */
+void pmg_fe_gauss(int n, double *x, double *w);
+void pmg_fe_gll(int n, double *x);
+void pmg_fe_lagrange(int n, const double *nodes, double x, double *val, double *der);
+void pmg_fe_pencil(int p, double *M, double *K);
+void pmg_fe_fastdiag(int p, double *S, double *lam);
+void pmg_fe_prolongation_h(int p, double *P);
+void pmg_fe_prolongation_p(int pc, int pf, double *P);
+void pmg_fe_diag_1d(int p, double *Md, double *Kd);
+void pmg_fe_dinv_table(int p, const double h[3], int dim, double *tab);
+
+struct pmg_context {
+  int device;
+  int rank, n_ranks;
+  cudaStream_t stream;
+  ncclComm_t comm;
+  int has_comm;
+  int64_t coarse_threshold;
+  double *work;      /* device: reduction workspace */
+  double *scalars;   /* device: small scalar slots */
+  double *h_scalars; /* pinned host mirror */
+  int sm_count;
+};
+
+/* one level's decomposition: z-slabs of cell layers, or everything on rank 0 */
+typedef struct pmg_layout {
+  int nx, ny, nz, degree;
+  int Nx, Ny, Nz;
+  int active;            /* this rank holds part of the level */
+  int gathered;          /* 1 = whole level on rank 0 */
+  int cz_lo, cz_hi;      /* owned cell layers */
+  int z0, nzl;           /* stored planes */
+  int z_own_lo, z_own_hi;/* owned planes */
+  int lower, upper;      /* neighbour ranks or -1 */
+  int64_t plane;         /* Nx*Ny */
+  int64_t n_local;       /* nzl*plane */
+  int64_t n_global;
+} pmg_layout;
+
+struct pmg_vector {
+  pmg_context *ctx;
+  pmg_layout lay;
+  double *d;
+};
+
+struct pmg_operator {
+  pmg_context *ctx;
+  int dim, degree, coefficient;
+  unsigned faces;
+  pmg_layout lay;
+  pmgk_level lv;
+  double *d_dinv_tab;
+  pmg_vector *dinv;      /* explicit inverse diagonal once compute_diagonal() ran */
+};
+
+struct pmg_transfer {
+  pmg_context *ctx;
+  int kind;
+  const pmg_operator *coarse, *fine;
+  double *d_P;
+  double *d_scratch;
+  pmg_vector *gather_buf; /* coarse-level vector in the fine level's layout when layouts differ */
+};
+
+struct pmg_chebyshev {
+  pmg_operator *op;
+  double smoothing_range;
+  int degree, eig_cg_n_iterations;
+  int initialized;
+  double lambda_min, lambda_max, theta, delta;
+  int cg_iterations;
+  pmg_vector *t0, *t1;   /* ping-pong work vectors */
+};
+
+int pmg_layout_make(pmg_context *ctx, int degree, int nx, int ny, int nz, pmg_layout *lay);
+int pmg_layout_same(const pmg_layout *a, const pmg_layout *b);
+int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector **v);
+int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d);
+int pmg_allreduce_sum(pmg_context *ctx, double *dev_scalar, int count);
+int pmg_chebyshev_estimate(pmg_chebyshev *s);
+/* fused smoother: u <- smooth(u, rhs); zero_guess => u is taken as 0 on entry.  tmp: work vector.
+   On return *result points at the vector that holds the smoothed iterate (u or tmp). */
+int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp,
+                         int zero_guess, pmg_vector **result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,240 @@
+/*
+ * pmg_smoother.c -- Chebyshev-Jacobi smoother of the C-ABI (host C).
+ *
+ * Stands in for deal.II's PreconditionChebyshev<LaplaceOperatorBase, Vector> with the
+ * DiagonalMatrix inner preconditioner, as configured by the reference drivers
+ * (source/geometric_multigrid/program.cc:267-285) and called from VCycleMultigrid::smooth
+ * (include/multigrid/portable_v_cycle_multigrid.h:116-125).  Numerical spec: DESIGN.md.
+ *
+ * B200-first: every Chebyshev step is ONE kernel (operator apply + Jacobi scaling + three-term
+ * update, csrc/pmg_apply_tile.h epilogue); the reference runs an apply kernel that writes A x to
+ * HBM followed by an unfused vector update that re-reads it.  The inverse diagonal comes from a
+ * (p+2)^3 table, not from a vector stream.  smooth(u, rhs) is evaluated as the Chebyshev iteration
+ * with initial guess u (algebraically identical to "r = rhs - A u; d = Cheb(r); u += d", one apply
+ * per step, no residual / correction vectors), so a smoothing step of degree k costs
+ * k fused passes of 32 B/DoF instead of k applies + (3k+2) vector passes.
+ */
+#include "pmg_internal.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+int pmg_chebyshev_create(pmg_operator *op, double smoothing_range, int degree, int eig_cg_n_iterations, pmg_chebyshev **out)
+{
+  if (!op || !out || eig_cg_n_iterations < 0 || (degree < 1 && degree != PMG_INVALID_DEGREE) || smoothing_range <= 0.0) {
+    pmg_set_error("chebyshev_create: bad arguments");
+    return PMG_ERR_ARG;
+  }
+  pmg_chebyshev *s = (pmg_chebyshev *)calloc(1, sizeof(*s));
+  if (!s) return PMG_ERR_NOMEM;
+  s->op = op; s->smoothing_range = smoothing_range; s->degree = degree; s->eig_cg_n_iterations = eig_cg_n_iterations;
+  PMG_CHECK(pmg_vector_create_layout(op->ctx, &op->lay, &s->t0));
+  PMG_CHECK(pmg_vector_create_layout(op->ctx, &op->lay, &s->t1));
+  *out = s;
+  return PMG_OK;
+}
+
+int pmg_chebyshev_destroy(pmg_chebyshev *s)
+{
+  if (!s) return PMG_OK;
+  pmg_vector_destroy(s->t0);
+  pmg_vector_destroy(s->t1);
+  free(s);
+  return PMG_OK;
+}
+
+int pmg_host_chebyshev_parameters(double lmin, double lmax_est, double smoothing_range, int degree_in,
+                                  double *theta, double *delta, int *degree_out)
+{
+  if (!theta || !delta || !degree_out) return PMG_ERR_ARG;
+  const double lmax = 1.2 * lmax_est; /* safety factor: CG is in general not converged */
+  const double alpha = (smoothing_range > 1.0) ? lmax / smoothing_range : fmin(0.9 * lmax, lmin);
+  int degree = degree_in;
+  if (degree == PMG_INVALID_DEGREE) {
+    /* Chebyshev error estimate (Varga, Matrix Iterative Analysis, sec. 5.1) */
+    const double actual_range = lmax / alpha;
+    const double sigma = (1.0 - sqrt(1.0 / actual_range)) / (1.0 + sqrt(1.0 / actual_range));
+    const double eps = smoothing_range;
+    degree = 1 + (int)(log(1.0 / eps + sqrt(1.0 / eps / eps - 1.0)) / log(1.0 / sigma));
+  }
+  *delta = (lmax - alpha) * 0.5;
+  *theta = (lmax + alpha) * 0.5;
+  *degree_out = degree;
+  return PMG_OK;
+}
+
+/* extreme eigenvalues of a symmetric tridiagonal matrix by Sturm-sequence bisection */
+static int sturm_count(int n, const double *d, const double *e, double x)
+{
+  int count = 0;
+  double q = 1.0;
+  for (int i = 0; i < n; ++i) {
+    const double e2 = (i > 0) ? e[i - 1] * e[i - 1] : 0.0;
+    q = d[i] - x - ((i > 0) ? e2 / q : 0.0);
+    if (q == 0.0) q = 1e-300;
+    if (q < 0.0) ++count;
+  }
+  return count; /* number of eigenvalues < x */
+}
+
+static double kth_eigenvalue(int n, const double *d, const double *e, int k, double lo, double hi)
+{
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid == lo || mid == hi) break;
+    if (sturm_count(n, d, e, mid) > k) hi = mid; else lo = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
+int pmg_host_tridiag_extreme_eigenvalues(int n, const double *diag, const double *offdiag, double *lmin, double *lmax)
+{
+  if (n < 1 || !diag || !lmin || !lmax || (n > 1 && !offdiag)) return PMG_ERR_ARG;
+  double lo = diag[0], hi = diag[0];
+  for (int i = 0; i < n; ++i) { /* Gershgorin bounds */
+    const double r = ((i > 0) ? fabs(offdiag[i - 1]) : 0.0) + ((i < n - 1) ? fabs(offdiag[i]) : 0.0);
+    if (diag[i] - r < lo) lo = diag[i] - r;
+    if (diag[i] + r > hi) hi = diag[i] + r;
+  }
+  const double pad = 1e-12 * fmax(fabs(lo), fabs(hi)) + 1e-300;
+  *lmin = kth_eigenvalue(n, diag, offdiag, 0, lo - pad, hi + pad);
+  *lmax = kth_eigenvalue(n, diag, offdiag, n - 1, lo - pad, hi + pad);
+  return PMG_OK;
+}
+
+/* PreconditionChebyshev::estimate_eigenvalues: Jacobi-preconditioned CG on A x = v from x = 0 with
+   v_i = (global_i mod 11) - mean, IterationNumberControl(eig_cg_n_iterations, 1e-10); eigenvalues of the
+   Lanczos matrix of iterations 1..it-1. */
+int pmg_chebyshev_estimate(pmg_chebyshev *s)
+{
+  pmg_operator *op = s->op;
+  pmg_context *ctx = op->ctx;
+  const pmg_layout *l = &op->lay;
+  double lmin = 1.0, lmax = 1.0;
+  s->cg_iterations = 0;
+  if (l->gathered && !l->active) { s->initialized = 1; return PMG_OK; } /* level lives on rank 0 */
+  if (s->eig_cg_n_iterations > 0) {
+    pmg_vector *r = NULL, *z = NULL, *pv = NULL, *Ap = NULL;
+    PMG_CHECK(pmg_vector_create_layout(ctx, l, &r));
+    PMG_CHECK(pmg_vector_create_layout(ctx, l, &z));
+    PMG_CHECK(pmg_vector_create_layout(ctx, l, &pv));
+    PMG_CHECK(pmg_vector_create_layout(ctx, l, &Ap));
+    const int max_it = s->eig_cg_n_iterations;
+    double *diag = (double *)calloc((size_t)max_it + 2, sizeof(double));
+    double *off = (double *)calloc((size_t)max_it + 2, sizeof(double));
+    int nt = 0, it = 0;
+    /* start vector on all stored planes (global index => identical on any rank count) */
+    PMG_CHECK(pmgk_set_mod11(r->d, l->plane * l->z0, l->n_local, ctx->stream));
+    double mean = 0.0, res = 0.0, rz = 0.0;
+    PMG_CHECK(pmg_vector_mean_value(r, &mean));
+    PMG_CHECK(pmgk_set(z->d, -mean, l->n_local, ctx->stream));
+    PMG_CHECK(pmg_vector_add(r, 1.0, z)); /* r = v - mean */
+    PMG_CHECK(pmg_vector_l2_norm(r, &res));
+    if (res > 1e-10) {
+      PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0, r->d, z->d, ctx->stream));
+      PMG_CHECK(pmg_vector_copy(pv, z));
+      PMG_CHECK(pmg_vector_dot(r, z, &rz));
+      double alpha_prev = 0.0, beta_prev = 0.0, eigen_beta_alpha = 0.0;
+      for (;;) {
+        ++it;
+        PMG_CHECK(pmg_laplace_operator_vmult(op, Ap, pv));
+        double pAp = 0.0;
+        PMG_CHECK(pmg_vector_dot(pv, Ap, &pAp));
+        const double alpha = rz / pAp;
+        PMG_CHECK(pmg_vector_add(r, -alpha, Ap));
+        PMG_CHECK(pmg_vector_l2_norm(r, &res));
+        if (it > 1) {
+          diag[nt] = 1.0 / alpha_prev + eigen_beta_alpha;
+          eigen_beta_alpha = beta_prev / alpha_prev;
+          off[nt] = sqrt(beta_prev) / alpha_prev;
+          ++nt;
+        }
+        if (res <= 1e-10 || it >= max_it) break;
+        PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0, r->d, z->d, ctx->stream));
+        double rz_new = 0.0;
+        PMG_CHECK(pmg_vector_dot(r, z, &rz_new));
+        const double beta = rz_new / rz;
+        PMG_CHECK(pmg_vector_sadd(pv, beta, 1.0, z));
+        rz = rz_new;
+        alpha_prev = alpha; beta_prev = beta;
+      }
+    }
+    s->cg_iterations = it;
+    if (nt > 0) PMG_CHECK(pmg_host_tridiag_extreme_eigenvalues(nt, diag, off, &lmin, &lmax));
+    free(diag); free(off);
+    pmg_vector_destroy(r); pmg_vector_destroy(z); pmg_vector_destroy(pv); pmg_vector_destroy(Ap);
+  }
+  int degree = s->degree;
+  PMG_CHECK(pmg_host_chebyshev_parameters(lmin, lmax, s->smoothing_range, s->degree, &s->theta, &s->delta, &degree));
+  s->degree = degree;
+  s->lambda_min = lmin;
+  s->lambda_max = 1.2 * lmax;
+  s->initialized = 1;
+  return PMG_OK;
+}
+
+int pmg_chebyshev_info(pmg_chebyshev *s, double *lambda_min, double *lambda_max, int *degree, int *cg_iterations)
+{
+  if (!s) return PMG_ERR_ARG;
+  if (!s->initialized) PMG_CHECK(pmg_chebyshev_estimate(s));
+  if (lambda_min) *lambda_min = s->lambda_min;
+  if (lambda_max) *lambda_max = s->lambda_max;
+  if (degree) *degree = s->degree;
+  if (cg_iterations) *cg_iterations = s->cg_iterations;
+  return PMG_OK;
+}
+
+/* One smooth(): k = degree fused passes.  Buffers ping-pong between u and tmp; *result tells the
+   caller where the final iterate lives. */
+int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp, int zero_guess,
+                         pmg_vector **result)
+{
+  if (!s->initialized) PMG_CHECK(pmg_chebyshev_estimate(s));
+  pmg_operator *op = s->op;
+  pmg_context *ctx = op->ctx;
+  *result = u;
+  if (!op->lay.active) return PMG_OK;
+  const double theta = s->theta, delta = s->delta;
+  pmg_vector *cur = u, *other = tmp;
+  int other_is_xold = 0; /* does `other` hold the previous iterate? */
+  /* step 0: x1 = x0 + theta^-1 Dinv (rhs - A x0) */
+  if (zero_guess) {
+    PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0 / theta, rhs->d, cur->d, ctx->stream)); /* x1 in cur, x0 = 0 */
+  } else {
+    PMG_CHECK(pmg_halo_update(ctx, &cur->lay, cur->d));
+    PMG_CHECK(pmgk_apply(&op->lv, PMGK_CHEB_FIRST, cur->d, rhs->d, NULL, other->d, 0.0, 1.0 / theta, ctx->stream));
+    pmg_vector *t = cur; cur = other; other = t; /* cur = x1, other = x0 */
+    other_is_xold = 1;
+  }
+  if (s->degree >= 2 && fabs(delta) >= 1e-40) {
+    double rhok = delta / theta;
+    const double sigma = theta / delta;
+    for (int k = 0; k < s->degree - 1; ++k) {
+      const double rhokp = 1.0 / (2.0 * sigma - rhok);
+      const double factor1 = rhokp * rhok, factor2 = 2.0 * rhokp / delta;
+      rhok = rhokp;
+      /* x_{k+2} = x_{k+1} + f1 (x_{k+1} - x_k) + f2 Dinv (rhs - A x_{k+1}), written over x_k */
+      PMG_CHECK(pmg_halo_update(ctx, &cur->lay, cur->d));
+      PMG_CHECK(pmgk_apply(&op->lv, PMGK_CHEB_STEP, cur->d, rhs->d, other_is_xold ? other->d : NULL, other->d, factor1, factor2,
+                           ctx->stream));
+      pmg_vector *t = cur; cur = other; other = t;
+      other_is_xold = 1;
+    }
+  }
+  *result = cur;
+  return PMG_OK;
+}
+
+/* PreconditionChebyshev::vmult: dst = Cheb_k(src) from a zero initial guess */
+int pmg_chebyshev_vmult(pmg_chebyshev *s, pmg_vector *dst, const pmg_vector *src)
+{
+  if (!s || !dst || !src || dst == src) { pmg_set_error("chebyshev_vmult: bad arguments"); return PMG_ERR_ARG; }
+  if (!pmg_layout_same(&dst->lay, &s->op->lay) || !pmg_layout_same(&src->lay, &s->op->lay)) {
+    pmg_set_error("chebyshev_vmult: vectors are not initialised for the smoother's operator");
+    return PMG_ERR_ARG;
+  }
+  pmg_vector *res = NULL;
+  PMG_CHECK(pmg_chebyshev_smooth(s, dst, src, s->t0, 1, &res));
+  if (res != dst) PMG_CHECK(pmg_vector_copy(dst, res));
+  return PMG_OK;
+}

@@ -1,0 +1,333 @@
+/*
+ * pmg_vcycle.c -- VCycleMultigrid and the outer CG of the C-ABI (host C).
+ *
+ * Mirrors Portable::VCycleMultigrid (reference include/multigrid/portable_v_cycle_multigrid.h:
+ * ctor :66-77, vmult :79-94, smooth :96-126, v_cycle :128-190) and deal.II's SolverCG as the
+ * drivers call it (source/geometric_multigrid/program.cc:342-355).
+ *
+ * B200-first differences: all level vectors are allocated once (the reference allocates 2 device
+ * vectors per smooth() and 3 per level per cycle, :116-118,:163-176); smoothing steps are fused
+ * passes (pmg_smoother.c); the first pre-smoothing step of every level starts from a zero guess and
+ * skips A*0; after a warm-up call the whole cycle is replayed from one CUDA graph, which removes the
+ * launch latency that dominates the coarse levels (1..512 cells).
+ */
+#include "pmg_internal.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PMG_MAX_LEVELS 32
+
+struct pmg_vcycle {
+  pmg_context *ctx;
+  int n_levels, pre, post;
+  pmg_operator *op[PMG_MAX_LEVELS];
+  pmg_transfer *tr[PMG_MAX_LEVELS];
+  pmg_chebyshev *sm[PMG_MAX_LEVELS];
+  pmg_vector *sol[PMG_MAX_LEVELS], *rhs[PMG_MAX_LEVELS], *tmp[PMG_MAX_LEVELS], *res[PMG_MAX_LEVELS];
+  int graph_enabled, calls;
+  cudaGraphExec_t graph_exec;
+  const double *graph_dst, *graph_src;
+  pmg_vector *host_dst, *host_src;
+  double *pinned_in, *pinned_out;
+  /* profiling */
+  int profiling;
+  int n_marks;
+  cudaEvent_t ev[4096];
+  int mark_level[4096], mark_cat[4096];
+};
+
+enum { CAT_SMOOTH = 0, CAT_TRANSFER = 1, CAT_HALO = 2, CAT_OTHER = 3 };
+
+static int mark(pmg_vcycle *v, int level, int cat)
+{
+  if (!v->profiling) return PMG_OK;
+  if (v->n_marks >= 4096) return PMG_OK;
+  const int i = v->n_marks++;
+  PMG_CUDA(cudaEventCreate(&v->ev[i]));
+  PMG_CUDA(cudaEventRecord(v->ev[i], v->ctx->stream));
+  v->mark_level[i] = level; v->mark_cat[i] = cat;
+  return PMG_OK;
+}
+
+int pmg_vcycle_create(pmg_operator *const *ops, pmg_transfer *const *transfers, pmg_chebyshev *const *smoothers,
+                      int n_levels, int pre, int post, pmg_vcycle **out)
+{
+  if (!ops || !smoothers || !out || n_levels < 1 || n_levels > PMG_MAX_LEVELS || pre < 0 || post < 0 || (n_levels > 1 && !transfers)) {
+    pmg_set_error("vcycle_create: bad arguments");
+    return PMG_ERR_ARG;
+  }
+  pmg_vcycle *v = (pmg_vcycle *)calloc(1, sizeof(*v));
+  if (!v) return PMG_ERR_NOMEM;
+  v->ctx = ops[0]->ctx; v->n_levels = n_levels; v->pre = pre; v->post = post;
+  v->graph_enabled = 1;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!ops[l] || !smoothers[l] || smoothers[l]->op != ops[l] || (l > 0 && !transfers[l])) {
+      pmg_set_error("vcycle_create: level %d is incomplete or its smoother belongs to another operator", l);
+      free(v);
+      return PMG_ERR_ARG;
+    }
+    if (l > 0 && (transfers[l]->coarse != ops[l - 1] || transfers[l]->fine != ops[l])) {
+      pmg_set_error("vcycle_create: transfer %d does not connect levels %d and %d", l, l - 1, l);
+      free(v);
+      return PMG_ERR_ARG;
+    }
+    v->op[l] = ops[l]; v->tr[l] = (l > 0) ? transfers[l] : NULL; v->sm[l] = smoothers[l];
+  }
+  for (int l = 0; l < n_levels; ++l) {
+    PMG_CHECK(pmg_vector_create_layout(v->ctx, &ops[l]->lay, &v->tmp[l]));
+    PMG_CHECK(pmg_vector_create_layout(v->ctx, &ops[l]->lay, &v->res[l]));
+    if (l < n_levels - 1) {
+      PMG_CHECK(pmg_vector_create_layout(v->ctx, &ops[l]->lay, &v->sol[l]));
+      PMG_CHECK(pmg_vector_create_layout(v->ctx, &ops[l]->lay, &v->rhs[l]));
+    }
+  }
+  *out = v;
+  return PMG_OK;
+}
+
+int pmg_vcycle_destroy(pmg_vcycle *v)
+{
+  if (!v) return PMG_OK;
+  cudaStreamSynchronize(v->ctx->stream);
+  if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
+  for (int l = 0; l < v->n_levels; ++l) {
+    pmg_vector_destroy(v->tmp[l]); pmg_vector_destroy(v->res[l]);
+    pmg_vector_destroy(v->sol[l]); pmg_vector_destroy(v->rhs[l]);
+  }
+  pmg_vector_destroy(v->host_dst); pmg_vector_destroy(v->host_src);
+  if (v->pinned_in) cudaFreeHost(v->pinned_in);
+  if (v->pinned_out) cudaFreeHost(v->pinned_out);
+  free(v);
+  return PMG_OK;
+}
+
+int pmg_vcycle_set_graph(pmg_vcycle *v, int enable)
+{
+  if (!v) return PMG_ERR_ARG;
+  v->graph_enabled = enable ? 1 : 0;
+  return PMG_OK;
+}
+
+/* v_cycle (:128-190).  u holds the iterate on entry unless zero_guess; on return u holds the result. */
+static int v_cycle(pmg_vcycle *v, int level, pmg_vector *u, const pmg_vector *rhs, int zero_guess)
+{
+  pmg_vector *cur = u, *other = v->tmp[level], *r = NULL;
+  if (level == 0) {
+    /* coarsest level: one smooth() (:148-154) */
+    PMG_CHECK(mark(v, level, CAT_SMOOTH));
+    PMG_CHECK(pmg_chebyshev_smooth(v->sm[0], cur, rhs, other, zero_guess, &r));
+    if (r != u) PMG_CHECK(pmg_vector_copy(u, r));
+    return PMG_OK;
+  }
+  /* pre-smoothing (:157-160) */
+  PMG_CHECK(mark(v, level, CAT_SMOOTH));
+  int zg = zero_guess;
+  for (int s = 0; s < v->pre; ++s) {
+    PMG_CHECK(pmg_chebyshev_smooth(v->sm[level], cur, rhs, other, zg, &r));
+    if (r != cur) { other = cur; cur = r; }
+    zg = 0;
+  }
+  /* residual = src - A dst (:163-166), restricted to the next coarser level (:169-172) */
+  PMG_CHECK(mark(v, level, CAT_OTHER));
+  if (zg) PMG_CHECK(pmg_vector_copy(v->res[level], rhs)); /* no pre-smoothing and u = 0: residual = rhs */
+  else PMG_CHECK(pmg_laplace_operator_residual(v->op[level], v->res[level], rhs, cur));
+  PMG_CHECK(mark(v, level, CAT_TRANSFER));
+  PMG_CHECK(pmg_vector_set(v->rhs[level - 1], 0.0));
+  PMG_CHECK(pmg_transfer_restrict_and_add(v->tr[level], v->rhs[level - 1], v->res[level]));
+  /* coarse correction from a zero guess (:175-179) */
+  PMG_CHECK(v_cycle(v, level - 1, v->sol[level - 1], v->rhs[level - 1], 1));
+  /* prolongate and add (:182) */
+  PMG_CHECK(mark(v, level, CAT_TRANSFER));
+  if (zg) { PMG_CHECK(pmg_vector_set(cur, 0.0)); zg = 0; }
+  PMG_CHECK(pmg_transfer_prolongate_and_add(v->tr[level], cur, v->sol[level - 1]));
+  /* post-smoothing (:185-188) */
+  PMG_CHECK(mark(v, level, CAT_SMOOTH));
+  for (int s = 0; s < v->post; ++s) {
+    PMG_CHECK(pmg_chebyshev_smooth(v->sm[level], cur, rhs, other, 0, &r));
+    if (r != cur) { other = cur; cur = r; }
+  }
+  PMG_CHECK(mark(v, level, CAT_OTHER));
+  if (cur != u) PMG_CHECK(pmg_vector_copy(u, cur));
+  return PMG_OK;
+}
+
+static int ensure_initialized(pmg_vcycle *v)
+{
+  for (int l = 0; l < v->n_levels; ++l)
+    if (!v->sm[l]->initialized) PMG_CHECK(pmg_chebyshev_estimate(v->sm[l]));
+  return PMG_OK;
+}
+
+int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
+{
+  if (!v || !dst || !src || dst == src) { pmg_set_error("vcycle_vmult: bad arguments"); return PMG_ERR_ARG; }
+  const int top = v->n_levels - 1;
+  if (!pmg_layout_same(&dst->lay, &v->op[top]->lay) || !pmg_layout_same(&src->lay, &v->op[top]->lay)) {
+    pmg_set_error("vcycle_vmult: vectors are not initialised for the finest level");
+    return PMG_ERR_ARG;
+  }
+  PMG_CHECK(ensure_initialized(v));
+  pmg_context *ctx = v->ctx;
+  /* dst = 0 (:92) is implied: the cycle starts from a zero guess */
+  if (!v->graph_enabled || v->profiling) return v_cycle(v, top, dst, src, 1);
+  if (v->graph_exec && v->graph_dst == dst->d && v->graph_src == src->d) {
+    PMG_CUDA(cudaGraphLaunch(v->graph_exec, ctx->stream));
+    pmg_count_launch(1);
+    return PMG_OK;
+  }
+  if (v->calls++ == 0) return v_cycle(v, top, dst, src, 1); /* warm-up: sets kernel attributes outside capture */
+  if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = NULL; }
+  cudaGraph_t graph = NULL;
+  PMG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = v_cycle(v, top, dst, src, 1);
+  cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != PMG_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    v->graph_enabled = 0; /* fall back to plain stream launches of the same kernels */
+    return v_cycle(v, top, dst, src, 1);
+  }
+  ce = cudaGraphInstantiate(&v->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { cudaGetLastError(); v->graph_exec = NULL; v->graph_enabled = 0; return v_cycle(v, top, dst, src, 1); }
+  v->graph_dst = dst->d; v->graph_src = src->d;
+  PMG_CUDA(cudaGraphLaunch(v->graph_exec, ctx->stream));
+  pmg_count_launch(1);
+  return PMG_OK;
+}
+
+int pmg_vcycle_vmult_host(pmg_vcycle *v, double *dst_host, const double *src_host)
+{
+  if (!v || !dst_host || !src_host) return PMG_ERR_ARG;
+  const int top = v->n_levels - 1;
+  if (!v->host_dst) {
+    PMG_CHECK(pmg_vector_create_layout(v->ctx, &v->op[top]->lay, &v->host_dst));
+    PMG_CHECK(pmg_vector_create_layout(v->ctx, &v->op[top]->lay, &v->host_src));
+  }
+  PMG_CHECK(pmg_vector_import_host(v->host_src, src_host));
+  PMG_CHECK(pmg_vcycle_vmult(v, v->host_dst, v->host_src));
+  return pmg_vector_export_host(v->host_dst, dst_host);
+}
+
+int pmg_vcycle_profile(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src, double *out_ms, int cap_levels)
+{
+  if (!v || !out_ms || cap_levels < v->n_levels) return PMG_ERR_ARG;
+  PMG_CHECK(ensure_initialized(v));
+  memset(out_ms, 0, sizeof(double) * 4 * cap_levels);
+  v->profiling = 1; v->n_marks = 0;
+  int rc = pmg_vcycle_vmult(v, dst, src);
+  if (!rc) rc = mark(v, 0, -1);
+  v->profiling = 0;
+  if (rc) return rc;
+  PMG_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  for (int i = 0; i + 1 < v->n_marks; ++i) {
+    float ms = 0.f;
+    PMG_CUDA(cudaEventElapsedTime(&ms, v->ev[i], v->ev[i + 1]));
+    out_ms[v->mark_level[i] * 4 + v->mark_cat[i]] += ms;
+  }
+  for (int i = 0; i < v->n_marks; ++i) cudaEventDestroy(v->ev[i]);
+  v->n_marks = 0;
+  return PMG_OK;
+}
+
+/* ---- SolverCG ----------------------------------------------------------------------------- */
+int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_vcycle *precond,
+                 int max_it, double tol, int *last_step, double *history, int history_cap)
+{
+  if (!A || !x || !b || max_it < 0) { pmg_set_error("cg_solve: bad arguments"); return PMG_ERR_ARG; }
+  if (!pmg_layout_same(&x->lay, &A->lay) || !pmg_layout_same(&b->lay, &A->lay)) {
+    pmg_set_error("cg_solve: vectors are not initialised for the operator");
+    return PMG_ERR_ARG;
+  }
+  pmg_context *ctx = A->ctx;
+  const pmg_layout *l = &A->lay;
+  pmg_vector *r = NULL, *z = NULL, *p = NULL, *Ap = NULL;
+  PMG_CHECK(pmg_vector_create_layout(ctx, l, &r));
+  PMG_CHECK(pmg_vector_create_layout(ctx, l, &z));
+  PMG_CHECK(pmg_vector_create_layout(ctx, l, &p));
+  PMG_CHECK(pmg_vector_create_layout(ctx, l, &Ap));
+  int it = 0, converged = 0, rc = PMG_OK;
+  double res = 0.0, rz = 0.0;
+#define CG(call) do { rc = (call); if (rc != PMG_OK) goto done; } while (0)
+  /* r = b - A x; convergence check before the first iteration */
+  CG(pmg_laplace_operator_residual(A, r, b, x));
+  CG(pmg_vector_l2_norm(r, &res));
+  if (history && history_cap > 0) history[0] = res;
+  if (res <= tol) converged = 1;
+  if (!converged) {
+    if (precond) CG(pmg_vcycle_vmult(precond, z, r)); else CG(pmg_vector_copy(z, r));
+    CG(pmg_vector_copy(p, z));
+    CG(pmg_vector_dot(r, z, &rz));
+  }
+  while (!converged && it < max_it) {
+    ++it;
+    CG(pmg_laplace_operator_vmult(A, Ap, p));
+    double pAp = 0.0;
+    CG(pmg_vector_dot(p, Ap, &pAp));
+    const double alpha = rz / pAp;
+    /* x += alpha p; r -= alpha Ap; ||r||^2 in one pass */
+    ctx->h_scalars[8] = alpha;
+    if (l->active) {
+      if (cudaMemcpyAsync(ctx->scalars + 8, ctx->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
+      /* local update over all stored planes, reduction over owned planes only */
+      const int64_t lo = l->plane * (l->z_own_lo - l->z0), n_own = l->plane * (l->z_own_hi - l->z_own_lo);
+      CG(pmgk_cg_update_xr(x->d + lo, r->d + lo, p->d + lo, Ap->d + lo, ctx->scalars + 8, n_own, ctx->scalars, ctx->work, ctx->stream));
+    } else {
+      if (cudaMemsetAsync(ctx->scalars, 0, sizeof(double), ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
+    }
+    if (!l->gathered) CG(pmg_allreduce_sum(ctx, ctx->scalars, 1));
+    if (cudaMemcpyAsync(ctx->h_scalars, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
+    res = sqrt(ctx->h_scalars[0]);
+    if (history && it < history_cap) history[it] = res;
+    if (res <= tol) { converged = 1; break; }
+    if (precond) CG(pmg_vcycle_vmult(precond, z, r)); else CG(pmg_vector_copy(z, r));
+    double rz_new = 0.0;
+    CG(pmg_vector_dot(r, z, &rz_new));
+    const double beta = rz_new / rz;
+    CG(pmg_vector_sadd(p, beta, 1.0, z)); /* p = z + beta p */
+    rz = rz_new;
+  }
+#undef CG
+done:
+  if (last_step) *last_step = it;
+  pmg_vector_destroy(r); pmg_vector_destroy(z); pmg_vector_destroy(p); pmg_vector_destroy(Ap);
+  if (rc != PMG_OK) return rc;
+  if (!converged) { pmg_set_error("CG did not converge in %d iterations (residual %g, tolerance %g)", it, res, tol); return PMG_ERR_NOT_CONVERGED; }
+  return PMG_OK;
+}
+
+int pmg_microbench(pmg_context *ctx, double *fma, double *dmma, double *hbm)
+{
+  if (!ctx) return PMG_ERR_ARG;
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  if (fma) PMG_CHECK(pmgk_bench_fp64_fma(fma, ctx->stream));
+  if (dmma) PMG_CHECK(pmgk_bench_fp64_dmma(dmma, ctx->stream));
+  if (hbm) PMG_CHECK(pmgk_bench_hbm_copy(hbm, ctx->stream));
+  return PMG_OK;
+}
+
+/* ---- host-only helpers ------------------------------------------------------------------------ */
+int pmg_host_fastdiag_tables(int degree, double *S, double *lam)
+{
+  if (degree < 1 || degree > PMG_MAX_DEGREE || !S || !lam) return PMG_ERR_ARG;
+  pmg_fe_fastdiag(degree, S, lam);
+  return PMG_OK;
+}
+
+int pmg_host_pencil(int degree, double *M, double *K)
+{
+  if (degree < 1 || degree > PMG_MAX_DEGREE || !M || !K) return PMG_ERR_ARG;
+  pmg_fe_pencil(degree, M, K);
+  return PMG_OK;
+}
+
+int pmg_host_prolongation_1d(int kind, int degree_coarse, int degree_fine, double *P)
+{
+  if (!P || degree_coarse < 1 || degree_coarse > PMG_MAX_DEGREE) return PMG_ERR_ARG;
+  if (kind == 0) { pmg_fe_prolongation_h(degree_coarse, P); return PMG_OK; }
+  if (degree_fine <= degree_coarse || degree_fine > PMG_MAX_DEGREE) return PMG_ERR_ARG;
+  pmg_fe_prolongation_p(degree_coarse, degree_fine, P);
+  return PMG_OK;
+}

@@ -1,0 +1,278 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libpmg.so), against the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: operator apply <= 1e-12 relative in
+l2, identical CG / V-cycle iteration counts, residual histories <= 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import hierarchy_levels, rel_l2, splitmix_src
+
+pytestmark = pytest.mark.gpu
+
+APPLY_TOL = 1e-12
+HISTORY_TOL = 1e-10
+
+
+def _oracle_levels(oracle, levels, faces=0x3F):
+    return [oracle.MatrixFree(3, p, n, faces=faces) for (p, n) in levels]
+
+
+def _oracle_hierarchy(oracle, levels, **kw):
+    mfs = _oracle_levels(oracle, levels)
+    trs = []
+    for l in range(1, len(levels)):
+        kind = "h" if levels[l][0] == levels[l - 1][0] else "p"
+        trs.append(oracle.Transfer(mfs[l - 1], mfs[l], kind))
+    return mfs, trs, oracle.VCycle(mfs, trs, **kw)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_vmult_matches_oracle(p, pmg, ctx, oracle):
+    n = {1: (17, 16, 18), 2: (13, 14, 9), 3: (11, 10, 7), 4: (9, 8, 5)}.get(p, (5, 6, 4))
+    mf = oracle.MatrixFree(3, p, n)
+    src = splitmix_src(mf.n_dofs)  # non-zero on Dirichlet dofs on purpose: dst[c] = src[c] there
+    ref = mf.vmult(src)
+    op = pmg.LaplaceOperator(ctx, p, n)
+    assert op.m() == mf.n_dofs == op.n()
+    s, d = op.vector_from(src), op.initialize_dof_vector()
+    op.vmult(d, s)
+    out = d.export_host()
+    assert rel_l2(out, ref) <= APPLY_TOL
+    c = mf.constrained()
+    assert np.array_equal(out[c], src[c])  # identity on Dirichlet dofs, bit for bit
+    op.Tvmult(d, s)
+    assert np.array_equal(d.export_host(), out)  # Tvmult == vmult, deterministic
+
+
+@pytest.mark.parametrize("faces", [0x00, 0x15, 0x2A, 0x03, 0x30])
+def test_vmult_mixed_boundary(faces, pmg, ctx, oracle):
+    p, n = 3, (6, 5, 7)
+    mf = oracle.MatrixFree(3, p, n, faces=faces)
+    src = splitmix_src(mf.n_dofs, salt=faces)
+    op = pmg.LaplaceOperator(ctx, p, n, dirichlet_faces=faces)
+    s, d = op.vector_from(src), op.initialize_dof_vector()
+    op.vmult(d, s)
+    assert rel_l2(d.export_host(), mf.vmult(src)) <= APPLY_TOL
+
+
+def test_vmult_large_properties(pmg, ctx):
+    """Size-independent properties at a BASELINE-scale mesh (Q4, 48^3 cells, 7.2M DoFs)."""
+    p, n = 4, 48
+    op = pmg.LaplaceOperator(ctx, p, n)
+    N = op.m()
+    u, v = splitmix_src(N, salt=1), splitmix_src(N, salt=2)
+    du, dv = op.vector_from(u), op.vector_from(v)
+    Au, Av, Aw = op.initialize_dof_vector(), op.initialize_dof_vector(), op.initialize_dof_vector()
+    op.vmult(Au, du)
+    op.vmult(Av, dv)
+    # symmetry (on vectors vanishing on the boundary) and linearity
+    Nx = n * p + 1
+    g = np.arange(N)
+    x, y, z = g % Nx, (g // Nx) % Nx, g // (Nx * Nx)
+    bnd = (x == 0) | (x == Nx - 1) | (y == 0) | (y == Nx - 1) | (z == 0) | (z == Nx - 1)
+    u0, v0 = u.copy(), v.copy()
+    u0[bnd] = 0
+    v0[bnd] = 0
+    du.import_host(u0)
+    dv.import_host(v0)
+    op.vmult(Au, du)
+    op.vmult(Av, dv)
+    a, b = dv.dot(Au), du.dot(Av)
+    assert abs(a - b) <= 1e-12 * abs(a)
+    w = 0.3 * u0 - 1.7 * v0
+    dw = op.vector_from(w)
+    op.vmult(Aw, dw)
+    lin = 0.3 * Au.export_host() - 1.7 * Av.export_host()
+    assert rel_l2(Aw.export_host(), lin) <= 1e-13
+    # constants are in the kernel away from the boundary: (A 1)_i = 0 for interior rows not adjacent to it
+    one = np.ones(N)
+    one[bnd] = 0
+    d1 = op.vector_from(one)
+    op.vmult(Au, d1)
+    r = Au.export_host()
+    deep = (x >= p) & (x <= Nx - 1 - p) & (y >= p) & (y <= Nx - 1 - p) & (z >= p) & (z <= Nx - 1 - p)
+    assert np.abs(r[deep]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 6])
+def test_diagonal_and_el(p, pmg, ctx, oracle):
+    n = (4, 3, 5) if p < 6 else (2, 3, 2)
+    mf = oracle.MatrixFree(3, p, n)
+    ref = mf.compute_diagonal()
+    op = pmg.LaplaceOperator(ctx, p, n)
+    with pytest.raises(pmg.PmgError):
+        op.get_matrix_diagonal_inverse()
+    op.compute_diagonal()
+    d = op.get_matrix_diagonal_inverse().export_host()
+    assert rel_l2(d, ref) <= 1e-13
+    row = mf.n_dofs // 2 + 3
+    assert abs(op.el(row, row) - 1.0 / ref[row]) <= 1e-12 / ref[row]
+    with pytest.raises(pmg.PmgError):
+        op.el(row, row + 1)
+
+
+def test_residual_and_vector_ops(pmg, ctx, oracle):
+    p, n = 2, (5, 6, 4)
+    mf = oracle.MatrixFree(3, p, n)
+    N = mf.n_dofs
+    u, b = splitmix_src(N, salt=3), splitmix_src(N, salt=4)
+    op = pmg.LaplaceOperator(ctx, p, n)
+    du, db, dr = op.vector_from(u), op.vector_from(b), op.initialize_dof_vector()
+    op.residual(dr, db, du)
+    assert rel_l2(dr.export_host(), b - mf.vmult(u)) <= APPLY_TOL
+    assert abs(du.dot(db) - float(u @ b)) <= 1e-12 * np.linalg.norm(u) * np.linalg.norm(b)
+    assert abs(du.l2_norm() - np.linalg.norm(u)) <= 1e-13 * np.linalg.norm(u)
+    assert abs(du.mean_value() - u.mean()) <= 1e-14
+    du.sadd(0.5, -2.0, db)
+    assert rel_l2(du.export_host(), 0.5 * u - 2.0 * b) <= 1e-15
+    du.add(3.0, db)
+    assert rel_l2(du.export_host(), 0.5 * u + b) <= 1e-15
+    du.scale(2.0)
+    du.set(1.25)
+    assert np.all(du.export_host() == 1.25)
+    assert du.size() == N and du.locally_owned_size() == N
+
+
+@pytest.mark.parametrize("p,nc", [(1, (3, 4, 2)), (2, (3, 2, 4)), (3, (2, 3, 2)), (4, (2, 2, 3)), (5, (2, 1, 2))])
+def test_h_transfer_matches_oracle(p, nc, pmg, ctx, oracle):
+    nf = tuple(2 * c for c in nc)
+    mc, mf = oracle.MatrixFree(3, p, nc), oracle.MatrixFree(3, p, nf)
+    t_ref = oracle.Transfer(mc, mf, "h")
+    oc, of = pmg.LaplaceOperator(ctx, p, nc), pmg.LaplaceOperator(ctx, p, nf)
+    t = pmg.GeometricTransfer(oc, of)
+    xc, xf = splitmix_src(mc.n_dofs, salt=5), splitmix_src(mf.n_dofs, salt=6)
+    dst0 = splitmix_src(mf.n_dofs, salt=7)
+    ref = t_ref.prolongate_and_add(dst0.copy(), xc)
+    dc, df = oc.vector_from(xc), of.vector_from(dst0)
+    t.prolongate_and_add(df, dc)
+    assert rel_l2(df.export_host(), ref) <= 1e-13
+    dstc0 = splitmix_src(mc.n_dofs, salt=8)
+    ref = t_ref.restrict_and_add(dstc0.copy(), xf)
+    dc2, df2 = oc.vector_from(dstc0), of.vector_from(xf)
+    t.restrict_and_add(dc2, df2)
+    assert rel_l2(dc2.export_host(), ref) <= 1e-13
+
+
+@pytest.mark.parametrize("pc,pf", [(1, 2), (2, 4), (1, 4), (3, 4), (2, 3), (4, 7), (6, 7), (4, 8)])
+def test_p_transfer_matches_oracle(pc, pf, pmg, ctx, oracle):
+    n = (3, 2, 3)
+    mc, mf = oracle.MatrixFree(3, pc, n), oracle.MatrixFree(3, pf, n)
+    t_ref = oracle.Transfer(mc, mf, "p")
+    oc, of = pmg.LaplaceOperator(ctx, pc, n), pmg.LaplaceOperator(ctx, pf, n)
+    t = pmg.PolynomialTransfer(oc, of)
+    xc, xf = splitmix_src(mc.n_dofs, salt=9), splitmix_src(mf.n_dofs, salt=10)
+    dst0 = splitmix_src(mf.n_dofs, salt=11)
+    ref = t_ref.prolongate_and_add(dst0.copy(), xc)
+    dc, df = oc.vector_from(xc), of.vector_from(dst0)
+    t.prolongate_and_add(df, dc)
+    assert rel_l2(df.export_host(), ref) <= 1e-13
+    dstc0 = splitmix_src(mc.n_dofs, salt=12)
+    ref = t_ref.restrict_and_add(dstc0.copy(), xf)
+    dc2, df2 = oc.vector_from(dstc0), of.vector_from(xf)
+    t.restrict_and_add(dc2, df2)
+    assert rel_l2(dc2.export_host(), ref) <= 1e-13
+
+
+def test_transfer_rejects_incompatible_levels(pmg, ctx):
+    a, b = pmg.LaplaceOperator(ctx, 2, 4), pmg.LaplaceOperator(ctx, 2, 6)
+    with pytest.raises(pmg.PmgError):
+        pmg.GeometricTransfer(a, b)  # not one global refinement (reference AssertThrow)
+    with pytest.raises(pmg.PmgError):
+        pmg.PolynomialTransfer(a, a)
+    with pytest.raises(pmg.PmgError):
+        pmg.LaplaceOperator(ctx, 9, 4)  # outside the compiled degree range
+
+
+@pytest.mark.parametrize("p,n,deg", [(2, (6, 5, 4), 5), (3, (4, 4, 4), 3), (4, (3, 4, 3), 5), (1, (8, 8, 8), 1)])
+def test_chebyshev_matches_oracle(p, n, deg, pmg, ctx, oracle):
+    mf = oracle.MatrixFree(3, p, n)
+    src = splitmix_src(mf.n_dofs, mf.constrained(), salt=13)
+    ref, info = oracle.chebyshev_vmult(mf, src, degree=deg)
+    op = pmg.LaplaceOperator(ctx, p, n)
+    op.compute_diagonal()
+    sm = pmg.Chebyshev(op, 15.0, deg, 10)
+    s, d = op.vector_from(src), op.initialize_dof_vector()
+    sm.vmult(d, s)
+    got = sm.info()
+    assert got["cg_iterations"] == info["cg_iterations"]
+    assert abs(got["lambda_max"] - info["lambda_max"]) <= 1e-9 * info["lambda_max"]
+    assert abs(got["lambda_min"] - info["lambda_min"]) <= 1e-7 * max(info["lambda_min"], 1e-3)
+    assert rel_l2(d.export_host(), ref) <= 1e-11
+
+
+@pytest.mark.parametrize("kind,p,n", [("h", 2, 8), ("h", 3, 8), ("h", 1, 16), ("hp", 4, 8), ("hp", 3, 4)])
+def test_vcycle_and_cg_match_oracle(kind, p, n, pmg, ctx, oracle):
+    levels = hierarchy_levels(kind, p, n)
+    mfs, trs, vc_ref = _oracle_hierarchy(oracle, levels)
+    ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)
+    top = ops[-1]
+    # smoother set-up parity (eigenvalue estimates, auto degree on the coarsest level)
+    est = vc_ref.estimate()
+    for l, sm in enumerate(smoothers):
+        info = sm.info()
+        assert info["degree"] == est[l][2], (l, info, est[l])
+        assert info["cg_iterations"] == est[l][3]
+        assert abs(info["lambda_max"] - est[l][1]) <= 1e-8 * est[l][1]
+    # one V-cycle on a synthetic residual
+    r = splitmix_src(mfs[-1].n_dofs, mfs[-1].constrained(), salt=14)
+    z_ref = vc_ref.vmult(r)
+    dr, dz = top.vector_from(r), top.initialize_dof_vector()
+    for rep in range(3):  # eager warm-up, graph capture, graph replay must agree
+        mg.vmult(dz, dr)
+        assert rel_l2(dz.export_host(), z_ref) <= 1e-10, rep
+    # full solve: same iteration count, residual history within 1e-10 relative
+    b_ref = mfs[-1].assemble_rhs()
+    b = top.initialize_dof_vector()
+    top.assemble_rhs(b)
+    assert rel_l2(b.export_host(), b_ref) <= 1e-14
+    x_ref, it_ref, hist_ref, rc_ref = oracle.cg_solve(mfs[-1], b_ref, vc_ref)
+    x = top.initialize_dof_vector()
+    it, hist, rc = pmg.cg_solve(top, x, b, mg)
+    assert rc == 0 and rc_ref == 0
+    assert it == it_ref
+    assert np.all(np.abs(hist - hist_ref) <= HISTORY_TOL * hist_ref[0])
+    assert rel_l2(x.export_host(), x_ref) <= 1e-9
+    norm = top.solution_norm(x)
+    assert abs(norm - mfs[-1].l2_norm_solution(x_ref)) <= 1e-10
+    assert abs(norm - 0.0249871331) < 2e-4  # analytic ||u||_L2 for -Laplace u = 1 on the unit cube
+
+
+def test_vcycle_graph_vs_eager_bitwise(pmg, ctx):
+    levels = hierarchy_levels("h", 2, 16)
+    ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)
+    top = ops[-1]
+    r = splitmix_src(top.m(), salt=15)
+    dr, dz = top.vector_from(r), top.initialize_dof_vector()
+    mg.set_graph(False)
+    mg.vmult(dz, dr)
+    eager = dz.export_host()
+    mg.set_graph(True)
+    for _ in range(3):
+        mg.vmult(dz, dr)
+    assert np.array_equal(dz.export_host(), eager)  # deterministic kernels: bit-identical
+    prof = mg.profile(dz, dr)
+    assert prof.shape == (len(levels), 4) and prof.sum() > 0
+
+
+def test_host_buffer_entry_points(pmg, ctx, oracle):
+    p, n = 2, (6, 6, 6)
+    mf = oracle.MatrixFree(3, p, n)
+    src = splitmix_src(mf.n_dofs, salt=16)
+    op = pmg.LaplaceOperator(ctx, p, n)
+    out = np.empty(mf.n_dofs)
+    op.vmult_host(out, src)
+    assert rel_l2(out, mf.vmult(src)) <= APPLY_TOL
+
+
+def test_error_paths(pmg, ctx):
+    a, b = pmg.LaplaceOperator(ctx, 2, 4), pmg.LaplaceOperator(ctx, 3, 4)
+    va, vb = a.initialize_dof_vector(), b.initialize_dof_vector()
+    with pytest.raises(pmg.PmgError):
+        a.vmult(va, vb)  # vector of another level
+    with pytest.raises(pmg.PmgError):
+        a.vmult(va, va)  # aliasing
+    with pytest.raises(pmg.PmgError):
+        va.add(1.0, vb)
+    with pytest.raises(pmg.PmgError):
+        pmg.LaplaceOperator(ctx, 2, 4, dim=2)
