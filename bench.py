@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- GDoF/s of the matrix-free multigrid hot path on B200 (contract: see task prompt 4).
+
+A step = one V-cycle (VCycleMultigrid::vmult, reference include/multigrid/portable_v_cycle_multigrid.h:79-94)
+on BASELINE.json configs[1]: 3-D Poisson, Q4, 64^3 cells (16 974 593 DoFs), polynomial multigrid
+p = 4 -> 2 -> 1 followed by geometric levels down to one cell, V(2,2), Chebyshev(5)-Jacobi smoothing with
+the reference drivers' parameters.  `value` = fine-level DoFs / device time per V-cycle, inputs resident in
+HBM.  `e2e` = the same through the C-ABI's host-buffer entry (pmg_vcycle_vmult_host: H2D of the residual
+from pinned memory, V-cycle, D2H of the correction).  `roofline` = the dominant kernel (the fused
+Chebyshev step on the finest level) timed alone with CUDA events on the library's stream.
+`--impl reference` times the reference's CPU algorithm (the oracle port: the reference itself cannot be
+compiled here) on the host cores for the same metric, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "portable-multigrid_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "GDoF/s of one multigrid V-cycle (fine-level DoFs / time); operator-apply GDoF/s in apply_gdofs"
+UNIT = "GDoF/s"
+DEGREE = 4
+CELLS = 64
+CPU_SAMPLE_CELLS = 16
+
+
+def scaled_cells(n, world):
+    """Weak scaling: per-GPU work fixed; cells doubled per direction z, y, x in turn."""
+    c = [n, n, n]
+    d, w = 2, world
+    while w > 1:
+        c[d] *= 2
+        d = (d - 1) % 3
+        w //= 2
+    return tuple(c)
+
+
+def hp_levels(p, cells):
+    """(degree, (nx,ny,nz)) coarse -> fine: p -> p/2 -> .. -> 1 on the fine mesh, then geometric levels."""
+    degs = [p]
+    while degs[-1] > 1:
+        degs.append(max(1, degs[-1] // 2))
+    levels = [(d, tuple(cells)) for d in degs]
+    c = list(cells)
+    while all(x % 2 == 0 for x in c) and min(c) > 1:
+        c = [x // 2 for x in c]
+        levels.append((1, tuple(c)))
+    return levels[::-1]
+
+
+def workload_name(p, cells, world):
+    nd = 1
+    for c in cells:
+        nd *= c * p + 1
+    return ("3D Poisson Q%d, %dx%dx%d cells (%d DoFs), hp-multigrid p=4->2->1 + geometric levels, V(2,2) "
+            "Chebyshev(5)-Jacobi, one V-cycle per step" % (p, cells[0], cells[1], cells[2], nd)), nd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_cheb_step_q4.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def run_reference(args):
+    """CPU arm: the oracle's V-cycle (port of the reference algorithm in the reference's data layout) on all
+    host threads, bounded sample: same hierarchy shape at CPU_SAMPLE_CELLS^3 cells."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import pyoracle as O
+    from helpers import splitmix_src
+
+    try:
+        O.build(native=True)
+        O.use_native()
+        kind = "port (-march=native)"
+    except Exception:
+        kind = "port"
+    res = cpu_vcycle(O, args.steps, args.warmup)
+    name, _ = workload_name(DEGREE, (CELLS,) * 3, 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "timing": "host wall clock around the oracle's V-cycle"},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"], "build": kind},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_vcycle(O, steps, warmup):
+    import numpy as np
+    from helpers import splitmix_src
+
+    levels = hp_levels(DEGREE, (CPU_SAMPLE_CELLS,) * 3)
+    mfs = [O.MatrixFree(3, p, c) for (p, c) in levels]
+    trs = [O.Transfer(mfs[l - 1], mfs[l], "h" if levels[l][0] == levels[l - 1][0] else "p") for l in range(1, len(levels))]
+    vc = O.VCycle(mfs, trs)
+    vc.estimate()
+    n = mfs[-1].n_dofs
+    r = splitmix_src(n, mfs[-1].constrained())
+    for _ in range(max(1, min(warmup, 2))):
+        vc.vmult(r)
+    k = max(1, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        vc.vmult(r)
+    dt = (time.perf_counter() - t0) / k
+    t0 = time.perf_counter()
+    for _ in range(3):
+        mfs[-1].vmult(r)
+    dta = (time.perf_counter() - t0) / 3
+    return {"value": n / dt / 1e9, "ms_per_step": dt * 1e3, "cores": O.num_threads(), "apply_gdofs": n / dta / 1e9,
+            "sample": "same hierarchy at %d^3 cells (%d DoFs), %d V-cycles; reference data layout "
+                      "(stored indices, masks, per-q-point Jacobians)" % (CPU_SAMPLE_CELLS, n, k)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--degree", type=int, default=DEGREE)
+    ap.add_argument("--cells", type=int, default=CELLS)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import pmg_b200 as G
+    from helpers import splitmix_src
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        obj = [G.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+    ctx = G.Context(local, rank, world, nccl_id)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    p = args.degree
+    cells = scaled_cells(args.cells, world)
+    levels = hp_levels(p, cells)
+    name, n_dofs = workload_name(p, cells, world)
+    ops, transfers, smoothers, mg = G.build_hierarchy(ctx, levels)
+    top = ops[-1]
+    r_host = splitmix_src(n_dofs)
+    r, z = top.vector_from(r_host), top.initialize_dof_vector()
+    for s in smoothers:
+        s.info()  # eigenvalue estimates outside the timed region (setup, as in the reference's first vmult)
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / k)
+
+    # kernels per V-cycle, counted on an eager (non-graph) cycle
+    mg.set_graph(False)
+    c0 = ctx.launch_count()
+    mg.vmult(z, r)
+    ctx.sync()
+    launches_per_cycle = ctx.launch_count() - c0
+    mg.set_graph(True)
+    for _ in range(max(args.warmup, 3)):
+        mg.vmult(z, r)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: mg.vmult(z, r), args.steps)
+    value = n_dofs / (ms * 1e-3) / 1e9
+
+    # operator apply alone (LaplaceOperator::vmult), and the dominant kernel of the cycle
+    u, b, xo = top.vector_from(splitmix_src(n_dofs, salt=1)), top.vector_from(splitmix_src(n_dofs, salt=2)), top.initialize_dof_vector()
+    for _ in range(3):
+        top.vmult(z, u)
+    ms_apply = timed(lambda: top.vmult(z, u), 20)
+    for _ in range(3):
+        top.chebyshev_step(xo, u, xo, b, 0.3, 0.1)
+    ms_step = timed(lambda: top.chebyshev_step(xo, u, xo, b, 0.3, 0.1), 20)
+
+    # end to end through the host-buffer entry point: pinned host memory, H2D + V-cycle + D2H every step
+    n_local_bytes = n_dofs * 8
+    e2e = None
+    if world == 1:
+        src_pin = torch.from_numpy(r_host).pin_memory()
+        dst_pin = torch.empty(n_dofs, dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            mg.vmult_host(dst_pin.data_ptr(), src_pin.data_ptr())
+        k = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            mg.vmult_host(dst_pin.data_ptr(), src_pin.data_ptr())  # returns after the D2H copy completed
+        dt = (time.perf_counter() - t0) / k
+        e2e = {"value": n_dofs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_local_bytes, "d2h_bytes_per_step": n_local_bytes,
+               "ms_per_step": dt * 1e3, "checksum": float(dst_pin.double().abs().sum())}
+    else:
+        # distributed: every rank uploads its slab and downloads the assembled correction
+        src_np = r_host
+        dst_np = np.empty(n_dofs)
+        for _ in range(1):
+            mg.vmult_host(dst_np, src_np)
+        k = 3
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            mg.vmult_host(dst_np, src_np)
+        dt = max_over_ranks((time.perf_counter() - t0) / k)
+        e2e = {"value": n_dofs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_local_bytes // world,
+               "d2h_bytes_per_step": n_local_bytes, "ms_per_step": dt * 1e3, "note": "pageable host buffers, export = allgather"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    peak, peak_src = measured_peaks()
+    n_local = n_dofs / world
+    algo_bytes = 32.0 * n_local  # fused Chebyshev step: read u, x_old, b; write x_new (Dinv is a table)
+    achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+    sweeps_flops = 0.0
+    n1 = p + 1
+    # flops of the kernel as written: per (cell, line) item  2*(p + 3*n1 + p... ) see DESIGN.md; per cell:
+    per_cell = 2.0 * (2 * p * n1 ** 3 + 4 * n1 ** 4) + 3.0 * n1 ** 3
+    fp64 = None
+    try:
+        mb = ctx.microbench() if rank == 0 else None
+    except Exception:
+        mb = None
+    if mb:
+        cells_total = cells[0] * cells[1] * cells[2] / world
+        fl = per_cell * cells_total
+        fp64 = {"flops_per_launch": fl, "achieved_tflops": fl / (ms_step * 1e-3) / 1e12, "peak_fma_tflops": mb["fp64_fma_tflops"],
+                "peak_dmma_tflops": mb["fp64_dmma_tflops"], "frac": fl / (ms_step * 1e-3) / 1e12 / mb["fp64_fma_tflops"],
+                "hbm_copy_gbs_here": mb["hbm_copy_gbs"], "note": "useful flops of owned cells; halo recompute not counted"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "levels": [[d, list(c)] for d, c in levels], "cache": "inputs larger than L2 (3-4 fine vectors of %.0f MB each)" % (n_local_bytes / world / 1e6),
+                   "parallelism": "z-slabs x%d" % world, "cuda_graph": True},
+        "apply_gdofs": n_dofs / (ms_apply * 1e-3) / 1e9, "apply_ms": ms_apply,
+        "apply_hbm_frac": 16.0 * n_local / (ms_apply * 1e-3) / 1e9 / peak,
+        "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
+        "clocks": clocks,
+        "roofline": {"kernel": "pmg_apply_kernel<%d> (fused Chebyshev step, finest level)" % p, "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_dof": 32, "ms_per_launch": ms_step, "fp64": fp64},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import pyoracle as O
+
+            try:
+                O.build(native=True)
+                O.use_native()
+            except Exception:
+                pass
+            res = cpu_vcycle(O, 3, 1)
+            line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"],
+                                    "apply_gdofs": res["apply_gdofs"]}
+        except Exception as e:  # the baseline is a reported number, never a dependency of the product path
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

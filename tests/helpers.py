@@ -9,7 +9,7 @@ def rel_l2(a, b):
 
 def splitmix_src(n_dofs, constrained=None, salt=0):
     """Deterministic synthetic vector: 2*u01(splitmix64(i ^ GOLDEN)) - 1."""
-    i = (np.arange(n_dofs, dtype=np.uint64) + np.uint64(salt) * np.uint64(0x632BE59BD9B4E019)) ^ np.uint64(0x9E3779B97F4A7C15)
+    i = (np.arange(n_dofs, dtype=np.uint64) + np.uint64((salt * 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF)) ^ np.uint64(0x9E3779B97F4A7C15)
     with np.errstate(over="ignore"):
         z = i + np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
