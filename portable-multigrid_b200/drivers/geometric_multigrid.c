@@ -1,0 +1,41 @@
+/*
+ * geometric_multigrid.c -- C re-creation of the reference driver source/geometric_multigrid/program.cc
+ * on top of the C-ABI (include/pmg.h): 3-D unit cube, degrees 1..7, six refinement cycles
+ * (1, 8, ..., 32768 cells; program.cc:404-417), h-multigrid V(2,2) with Chebyshev(5)-Jacobi smoothing
+ * (:267-285, :342-343), CG to 1e-12 ||b|| (:345-352).  Prints the reference's lines (:189-199, :354-355, :395).
+ * Flags: --degree D (only that degree), --max-degree M (default 7), --cycles C (default 6),
+ *        --cheb-degree K (default 5; BASELINE config 1 uses 3), --pre/--post (default 2).
+ */
+#include "driver_common.h"
+
+static int run_degree(pmg_context *ctx, int degree, int cycles, int pre, int post, int cheb)
+{
+  printf("============== fe_degree = %d ============== \n\n", degree);
+  for (int cycle = 0; cycle < cycles; ++cycle) {
+    printf("\n\nCycle %d\n", cycle);
+    level_t lv[MAXL];
+    const int L = cycle + 1; /* create_geometric_coarsening_sequence: 1, 2, 4, ... cells per direction */
+    for (int l = 0; l < L; ++l) { lv[l].degree = degree; lv[l].n = 1 << l; }
+    printf(" Number of degrees of freedom: %lld (by level: ", (long long)pow((double)lv[L - 1].n * degree + 1, 3));
+    for (int l = 0; l < L; ++l) printf("%lld%s", (long long)pow((double)lv[l].n * degree + 1, 3), l == L - 1 ? ")" : ", ");
+    printf("\n");
+    if (solve_hierarchy(ctx, lv, L, pre, post, cheb)) return 1;
+    printf("\n");
+  }
+  return 0;
+}
+
+int main(int argc, char **argv)
+{
+  const int only = arg_int(argc, argv, "--degree", 0);
+  const int max_degree = arg_int(argc, argv, "--max-degree", 7);
+  const int cycles = arg_int(argc, argv, "--cycles", 6);
+  const int cheb = arg_int(argc, argv, "--cheb-degree", 5);
+  const int pre = arg_int(argc, argv, "--pre", 2), post = arg_int(argc, argv, "--post", 2);
+  pmg_context *ctx;
+  CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
+  for (int d = (only ? only : 1); d <= (only ? only : max_degree); ++d)
+    if (run_degree(ctx, d, cycles, pre, post, cheb)) return 1;
+  pmg_context_destroy(ctx);
+  return 0;
+}

@@ -1,0 +1,192 @@
+"""CPU tests of the product's host logic and of the CUDA tile program run under the host emulator.
+
+No compute entry of libpmg.so is called here (there is no GPU): the library must load, export every
+symbol include/*.h declares, fail loudly without a device, and its host-only helpers must agree with the
+oracle.  The kernels' index logic / ownership rules / fused epilogues are checked by executing the same
+source (csrc/pmg_apply_tile.h) thread by thread on the CPU (tests/emu)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2, splitmix_src
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dp = C.POINTER(C.c_double)
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+# ---- C-ABI surface ---------------------------------------------------------------------------------
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmgk?_[a-zA-Z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(pmg):
+    lib = pmg.lib()
+    names = _declared("pmg.h") + _declared("pmg_kernels.h")
+    assert len(names) > 80
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(pmg):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pmg.PmgError) as e:
+        pmg.Context(0)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "portable-multigrid_b200")
+    for d, _, files in os.walk(pkg):
+        if os.sep + "build" in d:
+            continue
+        for f in files:
+            if f.endswith((".c", ".h", ".cu", ".py", "Makefile")):
+                txt = open(os.path.join(d, f), errors="replace").read()
+                assert "pyoracle" not in txt and "liborc" not in txt and "orc.h" not in txt, os.path.join(d, f)
+
+
+# ---- host helpers vs oracle ------------------------------------------------------------------------
+@pytest.mark.parametrize("p", range(1, 9))
+def test_fastdiag_tables(p, pmg, oracle):
+    S, lam = pmg.host_fastdiag_tables(p)
+    M, K = pmg.host_pencil(p)
+    Sv, Dco, w = oracle.shape_tables(p)
+    Mo, Ko = Sv.T @ np.diag(w) @ Sv, (Dco @ Sv).T @ np.diag(w) @ (Dco @ Sv)  # the reference's quadrature
+    assert np.abs(M - Mo).max() < 1e-14 and np.abs(K - Ko).max() < 1e-11
+    assert np.abs(S.T @ S - M).max() < 1e-14
+    assert np.abs(S.T @ np.diag(lam) @ S - K).max() < 1e-11
+    assert lam[0] == 0.0 and np.all(np.diff(lam) > 0)
+    assert np.linalg.cond(S) < 40  # well conditioned change of basis: no accuracy lost
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+def test_prolongation_matrices(p, pmg, oracle):
+    assert np.abs(pmg.host_prolongation_1d(0, p) - oracle.h_prolongation_1d(p)).max() < 1e-14
+    for pf in range(p + 1, 9):
+        assert np.abs(pmg.host_prolongation_1d(1, p, pf) - oracle.p_prolongation_1d(p, pf)).max() < 1e-14
+
+
+def test_chebyshev_parameters_and_tridiag(pmg, oracle):
+    theta, delta, k = pmg.host_chebyshev_parameters(0.3, 1.9, 15.0, 5)
+    lmax = 1.2 * 1.9
+    assert k == 5 and abs(theta - 0.5 * (lmax + lmax / 15)) < 1e-15 and abs(delta - 0.5 * (lmax - lmax / 15)) < 1e-15
+    theta, delta, k = pmg.host_chebyshev_parameters(1.0, 1.0, 1e-3, pmg.PMG_INVALID_DEGREE)
+    assert k == 3 and abs(theta - 1.1) < 1e-15  # one-dof coarse level of the geometric driver
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 9, 40):
+        d, e = rng.standard_normal(n) + 3, rng.standard_normal(max(n - 1, 0))
+        ev = oracle.tridiag_eigenvalues(d, e)
+        lo, hi = pmg.host_tridiag_extreme_eigenvalues(d, e)
+        assert abs(lo - ev[0]) < 1e-11 and abs(hi - ev[-1]) < 1e-11
+
+
+def test_partition(pmg):
+    for nz, R in [(320, 8), (64, 2), (40, 4), (8, 8)]:
+        slabs = [pmg.host_partition(nz, R, r) for r in range(R)]
+        assert all(ok for _, _, ok in slabs)
+        assert slabs[0][0] == 0 and slabs[-1][1] == nz
+        assert all(slabs[r][1] == slabs[r + 1][0] for r in range(R - 1))
+        fine = [pmg.host_partition(2 * nz, R, r) for r in range(R)]
+        assert all(f[0] == 2 * c[0] and f[1] == 2 * c[1] for f, c in zip(fine, slabs))  # refinement keeps slabs nested
+    lo, hi, ok = pmg.host_partition(5, 2, 0)
+    assert not ok and (lo, hi) == (0, 5)  # not divisible: the level lives on rank 0
+    assert pmg.host_partition(5, 2, 1)[:2] == (0, 0)
+    assert pmg.host_partition(7, 1, 0) == (0, 7, True)
+
+
+# ---- the CUDA tile program under the host emulator --------------------------------------------------
+def _tables(emu, p, h):
+    n = p + 1
+    S, lam, tab = np.zeros(n * n), np.zeros(n), np.zeros((p + 2) ** 3)
+    emu.pmg_fe_fastdiag(C.c_int(p), P(S), P(lam))
+    emu.pmg_fe_dinv_table(C.c_int(p), P(np.asarray(h, dtype=np.float64)), C.c_int(3), P(tab))
+    return S, lam, tab
+
+
+def emu_apply(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, chunks=1, faces=0x3F, slab=None, dinv_vec=None, out=None):
+    nx, ny, nz = n
+    h = np.array([1.0 / nx, 1.0 / ny, 1.0 / nz])
+    S, lam, tab = _tables(emu, p, h)
+    Nz = nz * p + 1
+    z0, nzl, czlo, czhi, zol, zoh = (0, Nz, 0, nz, 0, Nz) if slab is None else slab
+    if out is None:
+        out = np.full(u.shape, np.nan)
+    rc = emu.emu_apply(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(S), P(lam), P(h), mode,
+                       P(u), P(b), P(xold), P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec), P(tab))
+    assert rc == 0
+    return out
+
+
+def slab_of(p, n, cz_lo, cz_hi):
+    """(z0, nzl, cz_lo, cz_hi, z_own_lo, z_own_hi) of the product's ghost layout (pmg_core.c)."""
+    Nz = n[2] * p + 1
+    z0 = 0 if cz_lo == 0 else cz_lo * p - p
+    z_end = Nz if cz_hi == n[2] else cz_hi * p + 1
+    return z0, z_end - z0, cz_lo, cz_hi, cz_lo * p, (Nz if cz_hi == n[2] else cz_hi * p)
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("small,chunks", [(1, 1), (1, 3), (0, 2)])
+def test_emulated_apply_matches_oracle(p, small, chunks, emu, oracle):
+    n = (5, 4, 3) if p < 5 else (3, 2, 3)
+    mf = oracle.MatrixFree(3, p, n)
+    u = splitmix_src(mf.n_dofs, salt=p)
+    out = emu_apply(emu, p, n, u, small=small, chunks=chunks)
+    assert not np.isnan(out).any()  # every dof is written by exactly one owner
+    assert rel_l2(out, mf.vmult(u)) < 1e-13
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_emulated_epilogues_and_faces(p, emu, oracle):
+    n = (4, 3, 4)
+    mf = oracle.MatrixFree(3, p, n)
+    u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (1, 2, 3))
+    Au, dinv = mf.vmult(u), mf.compute_diagonal()
+    f1, f2 = 0.37, 0.81
+    assert rel_l2(emu_apply(emu, p, n, u, mode=1, b=b), b - Au) < 1e-13
+    assert rel_l2(emu_apply(emu, p, n, u, mode=2, b=b, f2=f2), u + f2 * dinv * (b - Au)) < 1e-13
+    ref = u + f1 * (u - xo) + f2 * dinv * (b - Au)
+    assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=f1, f2=f2), ref) < 1e-13
+    x2 = xo.copy()
+    emu_apply(emu, p, n, u, mode=3, b=b, xold=x2, f1=f1, f2=f2, out=x2)  # x_old overwritten in place
+    assert rel_l2(x2, ref) < 1e-13
+    assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, f1=f1, f2=f2), u + f1 * u + f2 * dinv * (b - Au)) < 1e-13
+    assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=f1, f2=f2, dinv_vec=dinv), ref) < 1e-13
+    for faces in (0x00, 0x15, 0x2A, 0x03):
+        m2 = oracle.MatrixFree(3, p, n, faces=faces)
+        A2, d2 = m2.vmult(u), m2.compute_diagonal()
+        assert rel_l2(emu_apply(emu, p, n, u, faces=faces), A2) < 1e-13
+        assert rel_l2(emu_apply(emu, p, n, u, mode=2, b=b, f2=f2, faces=faces), u + f2 * d2 * (b - A2)) < 1e-13
+
+
+@pytest.mark.parametrize("p,splits", [(1, [(0, 2), (2, 4)]), (3, [(0, 1), (1, 3), (3, 4)]), (4, [(0, 2), (2, 4)])])
+def test_emulated_slabs_cover_the_serial_result(p, splits, emu, oracle):
+    """Each rank applies the operator to its z-slab (ghost layer below, ghost plane above): the owned parts
+    tile the serial result and nothing outside the owned planes is written."""
+    n = (3, 4, 4)
+    mf = oracle.MatrixFree(3, p, n)
+    u = splitmix_src(mf.n_dofs, salt=7)
+    ref = mf.vmult(u)
+    plane = mf.nd[0] * mf.nd[1]
+    got = np.full(mf.n_dofs, np.nan)
+    for lo, hi in splits:
+        z0, nzl, _, _, zol, zoh = sl = slab_of(p, n, lo, hi)
+        ul = u[z0 * plane:(z0 + nzl) * plane].copy()
+        ol = emu_apply(emu, p, n, ul, slab=sl, chunks=2)
+        owned = np.zeros(nzl * plane, bool)
+        owned[(zol - z0) * plane:(zoh - z0) * plane] = True
+        assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()
+        got[zol * plane:zoh * plane] = ol[owned]
+    assert rel_l2(got, ref) < 1e-13
