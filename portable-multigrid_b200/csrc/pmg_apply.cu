@@ -11,8 +11,8 @@ struct PmgDeviceExec {
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-template <int P, int BX, int BY>
-__global__ void __launch_bounds__(PmgApplyTile<P, BX, BY>::NT, 1)
+template <int P, int BX, int BY, int MINB>
+__global__ void __launch_bounds__(PmgApplyTile<P, BX, BY>::NT, MINB)
 pmg_apply_kernel(const __grid_constant__ PmgApplyParams<P> p)
 {
   using Tile = PmgApplyTile<P, BX, BY>;
@@ -42,7 +42,7 @@ static void choose_chunks(int tiles, int layers, int slots, int *n_chunks, int *
   *layers_per_chunk = (layers + best_c - 1) / best_c;
 }
 
-template <int P, int BX, int BY>
+template <int P, int BX, int BY, int MINB>
 static int launch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                   double *out, double f1, double f2, cudaStream_t stream, int *geom)
 {
@@ -61,8 +61,8 @@ static int launch(const pmgk_level *lv, int mode, const double *u, const double 
   static int configured = 0;
   static int ctas_per_sm = 1;
   if (!configured) {
-    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_apply_kernel<P, BX, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_apply_kernel<P, BX, BY>, Tile::NT, smem_bytes));
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_apply_kernel<P, BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_apply_kernel<P, BX, BY, MINB>, Tile::NT, smem_bytes));
     if (ctas_per_sm < 1) return PMG_ERR_CUDA;
     configured = 1;
   }
@@ -77,7 +77,7 @@ static int launch(const pmgk_level *lv, int mode, const double *u, const double 
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
   const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
   if (geom) { geom[0] = grid; geom[1] = Tile::NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
-  pmg_apply_kernel<P, BX, BY><<<grid, Tile::NT, smem_bytes, stream>>>(p);
+  pmg_apply_kernel<P, BX, BY, MINB><<<grid, Tile::NT, smem_bytes, stream>>>(p);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
@@ -87,17 +87,29 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
                     double *out, double f1, double f2, cudaStream_t s, int *geom)
 {
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
+#define PMG_LAUNCH(P, BX, BY, MINB) return launch<P, BX, BY, MINB>(lv, mode, u, b, xold, out, f1, f2, s, geom)
+  if (lv->tile_variant != 2) { /* default: smaller tiles, two CTAs per SM (variant 2 = one large CTA per SM) */
+    switch (lv->degree) {
+      case 1: PMG_LAUNCH(1, 10, 10, 2);
+      case 2: PMG_LAUNCH(2, 8, 8, 2);
+      case 3: PMG_LAUNCH(3, 7, 7, 2);
+      case 4: PMG_LAUNCH(4, 6, 6, 2);
+      case 5: PMG_LAUNCH(5, 5, 4, 2);
+      default: break;
+    }
+  }
   switch (lv->degree) {
-    case 1: return launch<1, 16, 16>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 2: return launch<2, 12, 12>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 3: return launch<3, 10, 10>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 4: return launch<4, 8, 8>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 5: return launch<5, 7, 7>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 6: return launch<6, 6, 6>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 7: return launch<7, 5, 5>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-    case 8: return launch<8, 4, 4>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+    case 1: PMG_LAUNCH(1, 16, 16, 1);
+    case 2: PMG_LAUNCH(2, 12, 12, 1);
+    case 3: PMG_LAUNCH(3, 10, 10, 1);
+    case 4: PMG_LAUNCH(4, 8, 8, 1);
+    case 5: PMG_LAUNCH(5, 7, 7, 1);
+    case 6: PMG_LAUNCH(6, 5, 5, 1);
+    case 7: PMG_LAUNCH(7, 4, 5, 1);
+    case 8: PMG_LAUNCH(8, 4, 4, 1);
     default: return PMG_ERR_UNSUPPORTED;
   }
+#undef PMG_LAUNCH
 }
 
 extern "C" int pmgk_apply(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,

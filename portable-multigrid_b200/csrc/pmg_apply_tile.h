@@ -85,7 +85,15 @@ struct PmgApplyTile {
   static constexpr int T1_SIZE = NITEM * STRIDE;
   static constexpr int OX = CXC * N1 + 1, OY = CYC * N1; // cell-local output plane (row padded)
   static constexpr int O_SIZE = P * OX * OY;
-  static constexpr int SMEM_DOUBLES = (T1_SIZE > O_SIZE) ? T1_SIZE : O_SIZE;
+  // exchange tile and output planes are separate buffers (3 barriers per layer) when both fit,
+  // otherwise the output planes alias the exchange tile (5 barriers per layer)
+  static constexpr bool ALIAS = (T1_SIZE + O_SIZE) * 8 > 200 * 1024;
+  static constexpr int O_OFFSET = ALIAS ? 0 : T1_SIZE;
+  static constexpr int SMEM_DOUBLES = ALIAS ? ((T1_SIZE > O_SIZE) ? T1_SIZE : O_SIZE) : T1_SIZE + O_SIZE;
+  // epilogue iteration space: owned dof columns of the tile incl. the optional high face
+  static constexpr int EW = BX * P + 1, EH = BY * P + 1;
+  static constexpr int ECOLS = EW * EH;
+  static constexpr int EITER = (ECOLS + NT - 1) / NT;
 
   struct ThreadState {
     double X[N1][N1]; // [k or m][a]
@@ -117,17 +125,17 @@ struct PmgApplyTile {
   static PMG_HD int item_offset(int tcx, int j, int tcy) { return (tcx + CXC * (j + N1 * tcy)) * STRIDE; }
 
   // load one x-line of plane gz and transform it along x: X[k][a] = sum_i S[a][i] u[i]
-  static PMG_HD void load_xfwd(const PmgApplyParams<P> &p, const ThreadState &st, int gz, double *Xk)
+  static PMG_HD void load_xfwd(const PmgApplyParams<P> &p, const ThreadState &st, const double *row, int gz, double *Xk)
   {
-    const bool zero_plane = (gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u));
     double v[N1];
-    if (zero_plane || st.zero_row) {
 #pragma unroll
-      for (int i = 0; i < N1; ++i) v[i] = 0.0;
-    } else {
-      const double *row = p.u + (int64_t)(gz - p.z0) * p.Nx * p.Ny + (int64_t)(st.cy * P + st.j) * p.Nx + st.cx * P;
+    for (int i = 0; i < N1; ++i) v[i] = row[i];
+    if (st.zero_row | st.zero_i0 | st.zero_iP | (gz == 0) | (gz == p.Nz - 1)) { // rare: Dirichlet values read as 0
+      const bool zero_plane = (gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u));
+      if (zero_plane || st.zero_row) {
 #pragma unroll
-      for (int i = 0; i < N1; ++i) v[i] = row[i];
+        for (int i = 0; i < N1; ++i) v[i] = 0.0;
+      }
       if (st.zero_i0) v[0] = 0.0;
       if (st.zero_iP) v[P] = 0.0;
     }
@@ -149,6 +157,8 @@ struct PmgApplyTile {
     for (int m = 0; m < N1; ++m)
 #pragma unroll
       for (int a = 0; a < N1; ++a) st.X[m][a] = 0.0;
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const double *row = p.u + (int64_t)(cz * P - p.z0) * plane + (int64_t)(st.cy * P + st.j) * p.Nx + st.cx * P;
 #pragma unroll
     for (int k = 0; k < N1; ++k) {
       double xk[N1];
@@ -156,7 +166,7 @@ struct PmgApplyTile {
 #pragma unroll
         for (int a = 0; a < N1; ++a) xk[a] = st.cin[a];
       } else {
-        load_xfwd(p, st, cz * P + k, xk);
+        load_xfwd(p, st, row + k * plane, cz * P + k, xk);
       }
       if (k == P) {
 #pragma unroll
@@ -204,7 +214,7 @@ struct PmgApplyTile {
     }
   }
 
-  // B1: item (cell, j) reads its slab back into registers
+  // B2: z-backward one plane at a time (+ carry), x-backward, publish cell-local output lines to O
   static PMG_HD void phase_back_read(ThreadState &st, const double *smem)
   {
     if (!st.valid) return;
@@ -215,10 +225,16 @@ struct PmgApplyTile {
       for (int a = 0; a < N1; ++a) st.X[m][a] = src[m * N1 + a];
   }
 
-  // B2: z-backward one plane at a time (+ carry), x-backward, publish cell-local output lines to O
   static PMG_HD void phase_back_write(const PmgApplyParams<P> &p, ThreadState &st, double *smem, bool first_layer, bool write_out)
   {
     if (!st.valid) return;
+    if (!ALIAS) {
+      const double *src = smem + item_offset(st.tcx, st.j, st.tcy);
+#pragma unroll
+      for (int m = 0; m < N1; ++m)
+#pragma unroll
+        for (int a = 0; a < N1; ++a) st.X[m][a] = src[m * N1 + a];
+    }
 #pragma unroll
     for (int k = 0; k < N1; ++k) {
       double xk[N1];
@@ -237,7 +253,7 @@ struct PmgApplyTile {
 #pragma unroll
         for (int a = 0; a < N1; ++a) st.cout[a] = xk[a];
       } else if (write_out) {
-        double *dst = smem + (k * OY + st.tcy * N1 + st.j) * OX + st.tcx * N1;
+        double *dst = smem + O_OFFSET + (k * OY + st.tcy * N1 + st.j) * OX + st.tcx * N1;
 #pragma unroll
         for (int i = 0; i < N1; ++i) {
           double s = 0.0;
@@ -253,7 +269,7 @@ struct PmgApplyTile {
   static PMG_HD void phase_flush(const PmgApplyParams<P> &p, ThreadState &st, double *smem)
   {
     if (!st.valid) return;
-    double *dst = smem + (st.tcy * N1 + st.j) * OX + st.tcx * N1;
+    double *dst = smem + O_OFFSET + (st.tcy * N1 + st.j) * OX + st.tcx * N1;
 #pragma unroll
     for (int i = 0; i < N1; ++i) {
       double s = 0.0;
@@ -263,68 +279,87 @@ struct PmgApplyTile {
     }
   }
 
-  // E: owner epilogue for planes gz0 .. gz0+nplanes-1 of this tile
-  static PMG_HD void phase_epilogue(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0, int nplanes)
+  // E: owner epilogue for planes gz0 .. gz0+NPL-1 of this tile.  The iteration space is the
+  // compile-time (BX*P+1) x (BY*P+1) grid of owned dof columns; everything that does not depend on the
+  // plane (gather offsets, global offset, boundary flags, table index) is computed once per column, and
+  // the global loads of all planes of a column are issued before any of them is used.
+  template <int MODE, int NPL>
+  static PMG_HD void epilogue_t(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0)
   {
-    const int gx_begin = cx0 * P, gy_begin = cy0 * P;
+    const double *O = smem + O_OFFSET;
     const int gx_end = (cx0 + BX >= p.nx) ? p.Nx : (cx0 + BX) * P;
     const int gy_end = (cy0 + BY >= p.ny) ? p.Ny : (cy0 + BY) * P;
-    const int wx = gx_end - gx_begin, wy = gy_end - gy_begin;
-    if (wx <= 0 || wy <= 0) return;
-    const int total = wx * wy * nplanes;
     constexpr int T = P + 2;
-    for (int idx = tid; idx < total; idx += NT) {
-      const int ix = idx % wx;
-      const int iy = (idx / wx) % wy;
-      const int k = idx / (wx * wy);
-      const int gx = gx_begin + ix, gy = gy_begin + iy, gz = gz0 + k;
-      if (gz < p.z_own_lo || gz >= p.z_own_hi) continue;
-      // gather the cell-local contributions
-      const int Xt = gx - (cx0 - 1) * P, Yt = gy - (cy0 - 1) * P; // tile-local dof coordinates
-      double y = 0.0;
-      const int tx1 = Xt / P, ixl1 = Xt % P;
-      const int ty1 = Yt / P, iyl1 = Yt % P;
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const bool have_xold = (MODE == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
 #pragma unroll
-      for (int sy = 0; sy < 2; ++sy) {
-        int tcy, jl;
-        if (sy == 0) { tcy = ty1; jl = iyl1; }
-        else { if (iyl1 != 0) continue; tcy = ty1 - 1; jl = P; }
-        const int cy = cy0 - 1 + tcy;
-        if (tcy < 0 || tcy >= CYC || cy < 0 || cy >= p.ny) continue;
+    for (int it = 0; it < EITER; ++it) {
+      const int col = tid + it * NT;
+      if (col >= ECOLS) break;
+      const int ix = col % EW, iy = col / EW;
+      const int gx = cx0 * P + ix, gy = cy0 * P + iy;
+      if (gx >= gx_end || gy >= gy_end) continue;
+      const int64_t g0 = (int64_t)(gz0 - p.z0) * plane + (int64_t)gy * p.Nx + gx;
+      // issue every global load of this column first
+      double uc[NPL], bb[NPL], xo[NPL];
+      bool act[NPL];
 #pragma unroll
-        for (int sx = 0; sx < 2; ++sx) {
-          int tcx, il;
-          if (sx == 0) { tcx = tx1; il = ixl1; }
-          else { if (ixl1 != 0) continue; tcx = tx1 - 1; il = P; }
-          const int cx = cx0 - 1 + tcx;
-          if (tcx < 0 || tcx >= CXC || cx < 0 || cx >= p.nx) continue;
-          y += smem[(k * OY + tcy * N1 + jl) * OX + tcx * N1 + il];
-        }
+      for (int k = 0; k < NPL; ++k) {
+        act[k] = (gz0 + k >= p.z_own_lo) && (gz0 + k < p.z_own_hi);
+        const int64_t g = act[k] ? g0 + k * plane : g0;
+        uc[k] = p.u[g];
+        bb[k] = (MODE != PMG_MODE_APPLY) ? p.b[g] : 0.0;
+        xo[k] = have_xold ? p.xold[g] : 0.0;
       }
-      const int64_t g = (int64_t)(gz - p.z0) * p.Nx * p.Ny + (int64_t)gy * p.Nx + gx;
-      const bool dir = (gx == 0 && (p.faces & 1u)) || (gx == p.Nx - 1 && (p.faces >> 1 & 1u)) ||
-                       (gy == 0 && (p.faces >> 2 & 1u)) || (gy == p.Ny - 1 && (p.faces >> 3 & 1u)) ||
-                       (gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u));
-      const double uc = p.u[g];
-      const double Au = dir ? uc : y;
-      double r;
-      if (p.mode == PMG_MODE_APPLY) {
-        r = Au;
-      } else if (p.mode == PMG_MODE_RESIDUAL) {
-        r = p.b[g] - Au;
-      } else {
-        double dinv;
-        if (dir) dinv = 1.0;
-        else if (p.dinv_vec) dinv = p.dinv_vec[g];
-        else dinv = p.dinv_tab[pmg_pos_type<P>(gx, p.Nx) + T * (pmg_pos_type<P>(gy, p.Ny) + T * pmg_pos_type<P>(gz, p.Nz))];
-        const double corr = p.f2 * dinv * (p.b[g] - Au);
-        if (p.mode == PMG_MODE_CHEB_FIRST) r = uc + corr;
-        else {
-          const double xo = p.xold ? p.xold[g] : 0.0;
-          r = uc + p.f1 * (uc - xo) + corr;
+      // cell-local contributions: tile-local dof coordinates are (ix + P, iy + P)
+      const int tx1 = ix / P + 1, il = ix % P, ty1 = iy / P + 1, jl = iy % P;
+      const bool vx0 = (tx1 < CXC) && (cx0 - 1 + tx1 < p.nx);
+      const bool vx1 = (il == 0) && (cx0 - 1 + tx1 - 1 >= 0);
+      const bool vy0 = (ty1 < CYC) && (cy0 - 1 + ty1 < p.ny);
+      const bool vy1 = (jl == 0) && (cy0 - 1 + ty1 - 1 >= 0);
+      const int ox0 = tx1 * N1 + il, ox1 = (tx1 - 1) * N1 + P;
+      const int oy0 = (ty1 * N1 + jl) * OX, oy1 = ((ty1 - 1) * N1 + P) * OX;
+      const bool dirxy = (gx == 0 && (p.faces & 1u)) || (gx == p.Nx - 1 && (p.faces >> 1 & 1u)) ||
+                         (gy == 0 && (p.faces >> 2 & 1u)) || (gy == p.Ny - 1 && (p.faces >> 3 & 1u));
+      const int tbase = pmg_pos_type<P>(gx, p.Nx) + T * pmg_pos_type<P>(gy, p.Ny);
+#pragma unroll
+      for (int k = 0; k < NPL; ++k) {
+        const int gz = gz0 + k;
+        const double *Ok = O + k * (OX * OY);
+        double y = 0.0;
+        if (vx0 && vy0) y += Ok[oy0 + ox0];
+        if (vx1 && vy0) y += Ok[oy0 + ox1];
+        if (vx0 && vy1) y += Ok[oy1 + ox0];
+        if (vx1 && vy1) y += Ok[oy1 + ox1];
+        const bool dir = dirxy || (gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u));
+        const double Au = dir ? uc[k] : y;
+        double r;
+        if (MODE == PMG_MODE_APPLY) {
+          r = Au;
+        } else if (MODE == PMG_MODE_RESIDUAL) {
+          r = bb[k] - Au;
+        } else {
+          double dinv;
+          if (dir) dinv = 1.0;
+          else if (p.dinv_vec) dinv = p.dinv_vec[g0 + k * plane];
+          else dinv = p.dinv_tab[tbase + T * T * pmg_pos_type<P>(gz, p.Nz)];
+          const double corr = p.f2 * dinv * (bb[k] - Au);
+          if (MODE == PMG_MODE_CHEB_FIRST) r = uc[k] + corr;
+          else r = uc[k] + p.f1 * (uc[k] - xo[k]) + corr;
         }
+        if (act[k]) p.out[g0 + k * plane] = r;
       }
-      p.out[g] = r;
+    }
+  }
+
+  template <int NPL>
+  static PMG_HD void phase_epilogue(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0)
+  {
+    switch (p.mode) {
+      case PMG_MODE_APPLY: epilogue_t<PMG_MODE_APPLY, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_RESIDUAL: epilogue_t<PMG_MODE_RESIDUAL, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_CHEB_FIRST: epilogue_t<PMG_MODE_CHEB_FIRST, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      default: epilogue_t<PMG_MODE_CHEB_STEP, NPL>(p, tid, smem, cx0, cy0, gz0); break;
     }
   }
 
@@ -352,20 +387,24 @@ struct PmgApplyTile {
       ex.sync();
       ex.for_each_thread([&](int, ThreadState &st) { phase_y(p, st, smem); });
       ex.sync();
-      ex.for_each_thread([&](int, ThreadState &st) { phase_back_read(st, smem); });
-      ex.sync();
-      ex.for_each_thread([&](int, ThreadState &st) { phase_back_write(p, st, smem, first, write_out); });
-      ex.sync();
-      if (write_out) {
-        ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue(p, tid, smem, cx0, cy0, cz * P, P); });
+      if (ALIAS) {
+        ex.for_each_thread([&](int, ThreadState &st) { phase_back_read(st, smem); });
         ex.sync();
       }
+      ex.for_each_thread([&](int, ThreadState &st) { phase_back_write(p, st, smem, first, write_out); });
+      ex.sync();
+      // !ALIAS: no barrier after the epilogue: the next layer's forward and y phases only touch T1, and the
+      // two barriers they end with order this read of O before the next write to it
+      if (write_out)
+        ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue<P>(p, tid, smem, cx0, cy0, cz * P); });
+      if (ALIAS) ex.sync();
     }
     // top plane of the slab (owned only by the chunk that ends at the top of the mesh)
     if (cz_end == p.cz_hi && cz_end * P < p.z_own_hi) {
+      ex.sync();
       ex.for_each_thread([&](int, ThreadState &st) { phase_flush(p, st, smem); });
       ex.sync();
-      ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue(p, tid, smem, cx0, cy0, cz_end * P, 1); });
+      ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue<1>(p, tid, smem, cx0, cy0, cz_end * P); });
     }
   }
 };

@@ -80,14 +80,14 @@ extern "C" int emu_apply(int degree, int small_tiles, int nx, int ny, int nz, un
     }
     return -3;
   }
-  switch (degree) { // the tiles pmg_apply.cu launches
-    case 1: go<1, 16, 16>(ARGS); return 0;
-    case 2: go<2, 12, 12>(ARGS); return 0;
-    case 3: go<3, 10, 10>(ARGS); return 0;
-    case 4: go<4, 8, 8>(ARGS); return 0;
-    case 5: go<5, 7, 7>(ARGS); return 0;
-    case 6: go<6, 6, 6>(ARGS); return 0;
-    case 7: go<7, 5, 5>(ARGS); return 0;
+  switch (degree) { // the tiles pmg_apply.cu launches by default
+    case 1: go<1, 10, 10>(ARGS); return 0;
+    case 2: go<2, 8, 8>(ARGS); return 0;
+    case 3: go<3, 7, 7>(ARGS); return 0;
+    case 4: go<4, 6, 6>(ARGS); return 0;
+    case 5: go<5, 5, 4>(ARGS); return 0;
+    case 6: go<6, 5, 5>(ARGS); return 0;
+    case 7: go<7, 4, 5>(ARGS); return 0;
     case 8: go<8, 4, 4>(ARGS); return 0;
   }
   return -3;
