@@ -81,9 +81,13 @@ struct PmgApplyTile {
   static constexpr int NCELL = CXC * CYC;
   static constexpr int NITEM = NCELL * N1;
   static constexpr int NT = ((NITEM + 31) / 32) * 32;
-  static constexpr int STRIDE = (N1 * N1) | 1;     // odd item stride: conflict-free 64-bit access
-  static constexpr int T1_SIZE = NITEM * STRIDE;
-  static constexpr int OX = CXC * N1 + 1, OY = CYC * N1; // cell-local output plane (row padded)
+  // exchange tile T1[m][item][a]: the a-block of an item is padded to an odd length so that lanes
+  // (= consecutive items) hit different banks; tools/bank_conflicts.py models the access patterns
+  static constexpr int AP = N1 | 1;
+  static constexpr int T1_SIZE = N1 * NITEM * AP;
+  static constexpr bool Y_A_FASTEST = (N1 % 2) == 1; // phase-Y lane mapping (a fastest for odd N1)
+  static constexpr int OXPAD = (P == 1 || P == 3 || P == 7) ? 1 : 0;
+  static constexpr int OX = CXC * N1 + OXPAD, OY = CYC * N1; // cell-local output plane
   static constexpr int O_SIZE = P * OX * OY;
   // exchange tile and output planes are separate buffers (3 barriers per layer) when both fit,
   // otherwise the output planes alias the exchange tile (5 barriers per layer)
@@ -94,6 +98,8 @@ struct PmgApplyTile {
   static constexpr int EW = BX * P + 1, EH = BY * P + 1;
   static constexpr int ECOLS = EW * EH;
   static constexpr int EITER = (ECOLS + NT - 1) / NT;
+  // issue the epilogue's global loads before the barrier that precedes it (needs 3*EITER*P doubles of registers)
+  static constexpr bool PREFETCH_EPI = false; // measured on B200: the extra live registers spill (p=4: 100 -> 844 B) and cost 1.6-2x
 
   struct ThreadState {
     double X[N1][N1]; // [k or m][a]
@@ -103,6 +109,8 @@ struct PmgApplyTile {
     int cx, cy;       // global cell
     int valid;        // cell inside the mesh and item < NITEM
     int zero_row, zero_i0, zero_iP;
+    // epilogue inputs of this thread's dof columns, loaded before the barrier that precedes the epilogue
+    double eu[EITER][P], eb[EITER][P], exo[EITER][P];
   };
 
   // ---- helpers ------------------------------------------------------------
@@ -122,7 +130,8 @@ struct PmgApplyTile {
     for (int a = 0; a < N1; ++a) { st.cin[a] = 0.0; st.cout[a] = 0.0; }
   }
 
-  static PMG_HD int item_offset(int tcx, int j, int tcy) { return (tcx + CXC * (j + N1 * tcy)) * STRIDE; }
+  static PMG_HD int item_index(int tcx, int j, int tcy) { return tcx + CXC * (j + N1 * tcy); }
+  static PMG_HD int t1_index(int item, int m, int a) { return (m * NITEM + item) * AP + a; }
 
   // load one x-line of plane gz and transform it along x: X[k][a] = sum_i S[a][i] u[i]
   static PMG_HD void load_xfwd(const PmgApplyParams<P> &p, const ThreadState &st, const double *row, int gz, double *Xk)
@@ -177,26 +186,33 @@ struct PmgApplyTile {
 #pragma unroll
         for (int a = 0; a < N1; ++a) st.X[m][a] += p.S[m * N1 + k] * xk[a];
     }
-    double *dst = smem + item_offset(st.tcx, st.j, st.tcy);
+    double *dst = smem + t1_index(item_index(st.tcx, st.j, st.tcy), 0, 0);
 #pragma unroll
     for (int m = 0; m < N1; ++m)
 #pragma unroll
-      for (int a = 0; a < N1; ++a) dst[m * N1 + a] = st.X[m][a];
+      for (int a = 0; a < N1; ++a) dst[m * (NITEM * AP) + a] = st.X[m][a];
   }
 
-  // Y: item (cell, a): y-forward, diagonal scaling, y-backward, in place in T1, one m-column at a time
-  static PMG_HD void phase_y(const PmgApplyParams<P> &p, const ThreadState &st, double *smem)
+  // Y: item (cell, a): y-forward, diagonal scaling, y-backward, in place in T1, one m-column at a time.
+  // The (cell, a) pair is decoded from the thread id independently of the (cell, j) decode of the other
+  // phases so that the lanes of a warp read consecutive words.
+  static PMG_HD void phase_y(const PmgApplyParams<P> &p, int tid, int cx0, int cy0, double *smem)
   {
-    if (!st.valid) return;
-    const int a = st.j; // this phase reads the item index as (cell, a)
+    if (tid >= NITEM) return;
+    int a, tcx, tcy;
+    if (Y_A_FASTEST) { a = tid % N1; tcx = (tid / N1) % CXC; tcy = tid / (N1 * CXC); }
+    else { tcx = tid % CXC; a = (tid / CXC) % N1; tcy = tid / (CXC * N1); }
+    const int cx = cx0 - 1 + tcx, cy = cy0 - 1 + tcy;
+    if (cx < 0 || cx >= p.nx || cy < 0 || cy >= p.ny) return;
     const double base = p.c[0] * p.lam[a];
-    double *col = smem + item_offset(st.tcx, 0, st.tcy) + a;
-    constexpr int JSTRIDE = CXC * STRIDE; // distance between consecutive j of one cell
+    double *col = smem + t1_index(item_index(tcx, 0, tcy), 0, a);
+    constexpr int JSTRIDE = CXC * AP;   // distance between consecutive j of one cell
+    constexpr int MSTRIDE = NITEM * AP; // distance between consecutive m
 #pragma unroll
     for (int m = 0; m < N1; ++m) {
       double T[N1], Y[N1];
 #pragma unroll
-      for (int j = 0; j < N1; ++j) T[j] = col[j * JSTRIDE + m * N1];
+      for (int j = 0; j < N1; ++j) T[j] = col[j * JSTRIDE + m * MSTRIDE];
 #pragma unroll
       for (int bb = 0; bb < N1; ++bb) {
         double s = 0.0;
@@ -209,31 +225,30 @@ struct PmgApplyTile {
         double s = 0.0;
 #pragma unroll
         for (int bb = 0; bb < N1; ++bb) s += p.S[bb * N1 + j] * Y[bb];
-        col[j * JSTRIDE + m * N1] = s;
+        col[j * JSTRIDE + m * MSTRIDE] = s;
       }
     }
   }
 
-  // B2: z-backward one plane at a time (+ carry), x-backward, publish cell-local output lines to O
   static PMG_HD void phase_back_read(ThreadState &st, const double *smem)
   {
     if (!st.valid) return;
-    const double *src = smem + item_offset(st.tcx, st.j, st.tcy);
+    const double *src = smem + t1_index(item_index(st.tcx, st.j, st.tcy), 0, 0);
 #pragma unroll
     for (int m = 0; m < N1; ++m)
 #pragma unroll
-      for (int a = 0; a < N1; ++a) st.X[m][a] = src[m * N1 + a];
+      for (int a = 0; a < N1; ++a) st.X[m][a] = src[m * (NITEM * AP) + a];
   }
 
   static PMG_HD void phase_back_write(const PmgApplyParams<P> &p, ThreadState &st, double *smem, bool first_layer, bool write_out)
   {
     if (!st.valid) return;
     if (!ALIAS) {
-      const double *src = smem + item_offset(st.tcx, st.j, st.tcy);
+      const double *src = smem + t1_index(item_index(st.tcx, st.j, st.tcy), 0, 0);
 #pragma unroll
       for (int m = 0; m < N1; ++m)
 #pragma unroll
-        for (int a = 0; a < N1; ++a) st.X[m][a] = src[m * N1 + a];
+        for (int a = 0; a < N1; ++a) st.X[m][a] = src[m * (NITEM * AP) + a];
     }
 #pragma unroll
     for (int k = 0; k < N1; ++k) {
@@ -279,12 +294,39 @@ struct PmgApplyTile {
     }
   }
 
+  // issue the epilogue's global loads (u, b, x_old at this thread's owned dof columns) for the P planes of
+  // layer cz; called at the end of the backward phase so that the barrier wait overlaps their latency
+  static PMG_HD void epilogue_prefetch(const PmgApplyParams<P> &p, int tid, ThreadState &st, int cx0, int cy0, int gz0)
+  {
+    const int gx_end = (cx0 + BX >= p.nx) ? p.Nx : (cx0 + BX) * P;
+    const int gy_end = (cy0 + BY >= p.ny) ? p.Ny : (cy0 + BY) * P;
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const bool need_b = (p.mode != PMG_MODE_APPLY);
+    const bool need_xo = (p.mode == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
+#pragma unroll
+    for (int it = 0; it < EITER; ++it) {
+      const int col = tid + it * NT;
+      const int ix = col % EW, iy = col / EW;
+      const int gx = cx0 * P + ix, gy = cy0 * P + iy;
+      const bool ok = (col < ECOLS) && (gx < gx_end) && (gy < gy_end);
+      const int64_t g0 = (int64_t)(gz0 - p.z0) * plane + (int64_t)gy * p.Nx + gx;
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const bool act = ok && (gz0 + k >= p.z_own_lo) && (gz0 + k < p.z_own_hi);
+        const int64_t g = g0 + k * plane;
+        st.eu[it][k] = act ? p.u[g] : 0.0;
+        st.eb[it][k] = (act && need_b) ? p.b[g] : 0.0;
+        st.exo[it][k] = (act && need_xo) ? p.xold[g] : 0.0;
+      }
+    }
+  }
+
   // E: owner epilogue for planes gz0 .. gz0+NPL-1 of this tile.  The iteration space is the
   // compile-time (BX*P+1) x (BY*P+1) grid of owned dof columns; everything that does not depend on the
   // plane (gather offsets, global offset, boundary flags, table index) is computed once per column, and
   // the global loads of all planes of a column are issued before any of them is used.
-  template <int MODE, int NPL>
-  static PMG_HD void epilogue_t(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0)
+  template <int MODE, int NPL, bool PREF>
+  static PMG_HD void epilogue_t(const PmgApplyParams<P> &p, int tid, const ThreadState &st, const double *smem, int cx0, int cy0, int gz0)
   {
     const double *O = smem + O_OFFSET;
     const int gx_end = (cx0 + BX >= p.nx) ? p.Nx : (cx0 + BX) * P;
@@ -306,10 +348,14 @@ struct PmgApplyTile {
 #pragma unroll
       for (int k = 0; k < NPL; ++k) {
         act[k] = (gz0 + k >= p.z_own_lo) && (gz0 + k < p.z_own_hi);
-        const int64_t g = act[k] ? g0 + k * plane : g0;
-        uc[k] = p.u[g];
-        bb[k] = (MODE != PMG_MODE_APPLY) ? p.b[g] : 0.0;
-        xo[k] = have_xold ? p.xold[g] : 0.0;
+        if (PREF) {
+          uc[k] = st.eu[it][k < P ? k : 0]; bb[k] = st.eb[it][k < P ? k : 0]; xo[k] = st.exo[it][k < P ? k : 0];
+        } else {
+          const int64_t g = act[k] ? g0 + k * plane : g0;
+          uc[k] = p.u[g];
+          bb[k] = (MODE != PMG_MODE_APPLY) ? p.b[g] : 0.0;
+          xo[k] = have_xold ? p.xold[g] : 0.0;
+        }
       }
       // cell-local contributions: tile-local dof coordinates are (ix + P, iy + P)
       const int tx1 = ix / P + 1, il = ix % P, ty1 = iy / P + 1, jl = iy % P;
@@ -352,14 +398,14 @@ struct PmgApplyTile {
     }
   }
 
-  template <int NPL>
-  static PMG_HD void phase_epilogue(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0)
+  template <int NPL, bool PREF>
+  static PMG_HD void phase_epilogue(const PmgApplyParams<P> &p, int tid, const ThreadState &st, const double *smem, int cx0, int cy0, int gz0)
   {
     switch (p.mode) {
-      case PMG_MODE_APPLY: epilogue_t<PMG_MODE_APPLY, NPL>(p, tid, smem, cx0, cy0, gz0); break;
-      case PMG_MODE_RESIDUAL: epilogue_t<PMG_MODE_RESIDUAL, NPL>(p, tid, smem, cx0, cy0, gz0); break;
-      case PMG_MODE_CHEB_FIRST: epilogue_t<PMG_MODE_CHEB_FIRST, NPL>(p, tid, smem, cx0, cy0, gz0); break;
-      default: epilogue_t<PMG_MODE_CHEB_STEP, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_APPLY: epilogue_t<PMG_MODE_APPLY, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_RESIDUAL: epilogue_t<PMG_MODE_RESIDUAL, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_CHEB_FIRST: epilogue_t<PMG_MODE_CHEB_FIRST, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
+      default: epilogue_t<PMG_MODE_CHEB_STEP, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
     }
   }
 
@@ -385,18 +431,21 @@ struct PmgApplyTile {
       const bool write_out = (cz >= cz_begin);
       ex.for_each_thread([&](int, ThreadState &st) { phase_forward(p, st, smem, cz, first); });
       ex.sync();
-      ex.for_each_thread([&](int, ThreadState &st) { phase_y(p, st, smem); });
+      ex.for_each_thread([&](int tid, ThreadState &) { phase_y(p, tid, cx0, cy0, smem); });
       ex.sync();
       if (ALIAS) {
         ex.for_each_thread([&](int, ThreadState &st) { phase_back_read(st, smem); });
         ex.sync();
       }
-      ex.for_each_thread([&](int, ThreadState &st) { phase_back_write(p, st, smem, first, write_out); });
+      ex.for_each_thread([&](int tid, ThreadState &st) {
+        phase_back_write(p, st, smem, first, write_out);
+        if (PREFETCH_EPI && write_out) epilogue_prefetch(p, tid, st, cx0, cy0, cz * P);
+      });
       ex.sync();
       // !ALIAS: no barrier after the epilogue: the next layer's forward and y phases only touch T1, and the
       // two barriers they end with order this read of O before the next write to it
       if (write_out)
-        ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue<P>(p, tid, smem, cx0, cy0, cz * P); });
+        ex.for_each_thread([&](int tid, ThreadState &st) { phase_epilogue<P, PREFETCH_EPI>(p, tid, st, smem, cx0, cy0, cz * P); });
       if (ALIAS) ex.sync();
     }
     // top plane of the slab (owned only by the chunk that ends at the top of the mesh)
@@ -404,7 +453,7 @@ struct PmgApplyTile {
       ex.sync();
       ex.for_each_thread([&](int, ThreadState &st) { phase_flush(p, st, smem); });
       ex.sync();
-      ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue<1>(p, tid, smem, cx0, cy0, cz_end * P); });
+      ex.for_each_thread([&](int tid, ThreadState &st) { phase_epilogue<1, false>(p, tid, st, smem, cx0, cy0, cz_end * P); });
     }
   }
 };
