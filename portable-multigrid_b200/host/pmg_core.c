@@ -224,7 +224,7 @@ int pmg_vector_locally_owned_size(const pmg_vector *v, int64_t *n)
 
 double *pmg_vector_device_ptr(pmg_vector *v) { return v ? v->d : NULL; }
 
-static double *owned_ptr(const pmg_vector *v) { return v->d + v->lay.plane * (v->lay.z_own_lo - v->lay.z0); }
+static double *owned_ptr(const pmg_vector *v) { return v->d ? v->d + v->lay.plane * (v->lay.z_own_lo - v->lay.z0) : NULL; }
 static int64_t owned_n(const pmg_vector *v) { return v->lay.plane * (v->lay.z_own_hi - v->lay.z_own_lo); }
 
 static int check_pair(const pmg_vector *a, const pmg_vector *b)
@@ -288,9 +288,10 @@ int pmg_vector_dot(const pmg_vector *x, const pmg_vector *y, double *result)
   PMG_CHECK(check_pair(x, y));
   if (!result) return PMG_ERR_ARG;
   pmg_context *ctx = x->ctx;
-  if (x->lay.gathered && !x->lay.active) { *result = 0.0; return PMG_OK; }
+  /* every rank takes part (a level gathered on rank 0 contributes 0 elsewhere), so all ranks see the same
+     value and stay in lock-step in the iterative solvers */
   PMG_CHECK(pmgk_dot(owned_ptr(x), owned_ptr(y), owned_n(x), ctx->scalars, ctx->work, ctx->stream));
-  if (!x->lay.gathered) PMG_CHECK(pmg_allreduce_sum(ctx, ctx->scalars, 1));
+  PMG_CHECK(pmg_allreduce_sum(ctx, ctx->scalars, 1));
   return fetch_scalar(ctx, 0, result);
 }
 
@@ -306,9 +307,8 @@ int pmg_vector_mean_value(const pmg_vector *x, double *result)
 {
   if (!x || !result) return PMG_ERR_ARG;
   pmg_context *ctx = x->ctx;
-  if (x->lay.gathered && !x->lay.active) { *result = 0.0; return PMG_OK; }
   PMG_CHECK(pmgk_sum(owned_ptr(x), owned_n(x), ctx->scalars, ctx->work, ctx->stream));
-  if (!x->lay.gathered) PMG_CHECK(pmg_allreduce_sum(ctx, ctx->scalars, 1));
+  PMG_CHECK(pmg_allreduce_sum(ctx, ctx->scalars, 1));
   double s = 0.0;
   PMG_CHECK(fetch_scalar(ctx, 0, &s));
   *result = s / (double)x->lay.n_global;

@@ -112,7 +112,6 @@ int pmg_chebyshev_estimate(pmg_chebyshev *s)
   const pmg_layout *l = &op->lay;
   double lmin = 1.0, lmax = 1.0;
   s->cg_iterations = 0;
-  if (l->gathered && !l->active) { s->initialized = 1; return PMG_OK; } /* level lives on rank 0 */
   if (s->eig_cg_n_iterations > 0) {
     pmg_vector *r = NULL, *z = NULL, *pv = NULL, *Ap = NULL;
     PMG_CHECK(pmg_vector_create_layout(ctx, l, &r));

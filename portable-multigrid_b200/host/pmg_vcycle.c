@@ -276,7 +276,7 @@ int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_
     } else {
       if (cudaMemsetAsync(ctx->scalars, 0, sizeof(double), ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
     }
-    if (!l->gathered) CG(pmg_allreduce_sum(ctx, ctx->scalars, 1));
+    CG(pmg_allreduce_sum(ctx, ctx->scalars, 1));
     if (cudaMemcpyAsync(ctx->h_scalars, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
     res = sqrt(ctx->h_scalars[0]);

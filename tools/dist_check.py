@@ -30,8 +30,8 @@ def main():
 
     def report(name, err, tol):
         nonlocal ok
-        if rank == 0:
-            print("%-44s %.3e %s" % (name, err, "ok" if err <= tol else "FAIL"), flush=True)
+        if rank == 0 or not (err <= tol):
+            print("[rank %d] %-44s %.3e %s" % (rank, name, err, "ok" if err <= tol else "FAIL"), flush=True)
         ok = ok and (err <= tol)
 
     import pyoracle as O
