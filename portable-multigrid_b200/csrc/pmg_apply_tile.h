@@ -33,6 +33,29 @@
 #define PMG_HD inline
 #endif
 
+// 8-byte asynchronous global -> shared copy (LDGSTS); a plain copy under the host emulator
+PMG_HD void pmg_cp_async8(double *dst_smem, const double *src_global)
+{
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_global) : "memory");
+#else
+  *dst_smem = *src_global;
+#endif
+}
+PMG_HD void pmg_cp_async_commit()
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+PMG_HD void pmg_cp_async_wait_all()
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
 enum PmgApplyMode {
   PMG_MODE_APPLY = 0,     // out = A u
   PMG_MODE_RESIDUAL = 1,  // out = b - A u
@@ -93,13 +116,18 @@ struct PmgApplyTile {
   // otherwise the output planes alias the exchange tile (5 barriers per layer)
   static constexpr bool ALIAS = (T1_SIZE + O_SIZE) * 8 > 200 * 1024;
   static constexpr int O_OFFSET = ALIAS ? 0 : T1_SIZE;
-  static constexpr int SMEM_DOUBLES = ALIAS ? ((T1_SIZE > O_SIZE) ? T1_SIZE : O_SIZE) : T1_SIZE + O_SIZE;
+  // input staging IN[k][y][x]: the P new dof planes of the NEXT cell layer, copied with cp.async while the
+  // current layer is computed; enabled when T1 + O + IN of two CTAs fit on one SM
+  static constexpr int CXD = CXC * P + 1, CYD = CYC * P + 1; // dof columns touched by the tile
+  static constexpr int IN_SIZE = P * CXD * CYD;
+  static constexpr bool STAGE_IN = false; // measured on B200 (p=2..4): 5-15 % slower than direct loads, which hit L1/L2
+  static constexpr int IN_OFFSET = T1_SIZE + O_SIZE;
+  static constexpr int SMEM_DOUBLES =
+    ALIAS ? ((T1_SIZE > O_SIZE) ? T1_SIZE : O_SIZE) : T1_SIZE + O_SIZE + (STAGE_IN ? IN_SIZE : 0);
   // epilogue iteration space: owned dof columns of the tile incl. the optional high face
   static constexpr int EW = BX * P + 1, EH = BY * P + 1;
   static constexpr int ECOLS = EW * EH;
   static constexpr int EITER = (ECOLS + NT - 1) / NT;
-  // issue the epilogue's global loads before the barrier that precedes it (needs 3*EITER*P doubles of registers)
-  static constexpr bool PREFETCH_EPI = false; // measured on B200: the extra live registers spill (p=4: 100 -> 844 B) and cost 1.6-2x
 
   struct ThreadState {
     double X[N1][N1]; // [k or m][a]
@@ -109,8 +137,6 @@ struct PmgApplyTile {
     int cx, cy;       // global cell
     int valid;        // cell inside the mesh and item < NITEM
     int zero_row, zero_i0, zero_iP;
-    // epilogue inputs of this thread's dof columns, loaded before the barrier that precedes the epilogue
-    double eu[EITER][P], eb[EITER][P], exo[EITER][P];
   };
 
   // ---- helpers ------------------------------------------------------------
@@ -157,6 +183,21 @@ struct PmgApplyTile {
     }
   }
 
+  // copy the P new dof planes of cell layer cz (global planes cz*P+1 .. cz*P+P, tile columns) into IN
+  static PMG_HD void stage_issue(const PmgApplyParams<P> &p, int tid, double *smem, int cx0, int cy0, int cz)
+  {
+    const int gx0 = (cx0 - 1) * P, gy0 = (cy0 - 1) * P;
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const double *base = p.u + (int64_t)(cz * P + 1 - p.z0) * plane;
+    double *in = smem + IN_OFFSET;
+    for (int e = tid; e < IN_SIZE; e += NT) {
+      const int x = e % CXD, y = (e / CXD) % CYD, k = e / (CXD * CYD);
+      const int gx = gx0 + x, gy = gy0 + y;
+      if (gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny) pmg_cp_async8(in + e, base + k * plane + (int64_t)gy * p.Nx + gx);
+    }
+    pmg_cp_async_commit();
+  }
+
   // ---- phases (one call per thread; separated by sync) ----------------------
   // F: load the layer's new planes, x-forward each, accumulate the z-forward sweep, publish to T1
   static PMG_HD void phase_forward(const PmgApplyParams<P> &p, ThreadState &st, double *smem, int cz, bool first_layer)
@@ -174,6 +215,8 @@ struct PmgApplyTile {
       if (k == 0 && !first_layer) {
 #pragma unroll
         for (int a = 0; a < N1; ++a) xk[a] = st.cin[a];
+      } else if (STAGE_IN && k > 0) {
+        load_xfwd(p, st, smem + IN_OFFSET + ((k - 1) * CYD + st.tcy * P + st.j) * CXD + st.tcx * P, cz * P + k, xk);
       } else {
         load_xfwd(p, st, row + k * plane, cz * P + k, xk);
       }
@@ -294,39 +337,12 @@ struct PmgApplyTile {
     }
   }
 
-  // issue the epilogue's global loads (u, b, x_old at this thread's owned dof columns) for the P planes of
-  // layer cz; called at the end of the backward phase so that the barrier wait overlaps their latency
-  static PMG_HD void epilogue_prefetch(const PmgApplyParams<P> &p, int tid, ThreadState &st, int cx0, int cy0, int gz0)
-  {
-    const int gx_end = (cx0 + BX >= p.nx) ? p.Nx : (cx0 + BX) * P;
-    const int gy_end = (cy0 + BY >= p.ny) ? p.Ny : (cy0 + BY) * P;
-    const int64_t plane = (int64_t)p.Nx * p.Ny;
-    const bool need_b = (p.mode != PMG_MODE_APPLY);
-    const bool need_xo = (p.mode == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
-#pragma unroll
-    for (int it = 0; it < EITER; ++it) {
-      const int col = tid + it * NT;
-      const int ix = col % EW, iy = col / EW;
-      const int gx = cx0 * P + ix, gy = cy0 * P + iy;
-      const bool ok = (col < ECOLS) && (gx < gx_end) && (gy < gy_end);
-      const int64_t g0 = (int64_t)(gz0 - p.z0) * plane + (int64_t)gy * p.Nx + gx;
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const bool act = ok && (gz0 + k >= p.z_own_lo) && (gz0 + k < p.z_own_hi);
-        const int64_t g = g0 + k * plane;
-        st.eu[it][k] = act ? p.u[g] : 0.0;
-        st.eb[it][k] = (act && need_b) ? p.b[g] : 0.0;
-        st.exo[it][k] = (act && need_xo) ? p.xold[g] : 0.0;
-      }
-    }
-  }
-
   // E: owner epilogue for planes gz0 .. gz0+NPL-1 of this tile.  The iteration space is the
   // compile-time (BX*P+1) x (BY*P+1) grid of owned dof columns; everything that does not depend on the
   // plane (gather offsets, global offset, boundary flags, table index) is computed once per column, and
   // the global loads of all planes of a column are issued before any of them is used.
-  template <int MODE, int NPL, bool PREF>
-  static PMG_HD void epilogue_t(const PmgApplyParams<P> &p, int tid, const ThreadState &st, const double *smem, int cx0, int cy0, int gz0)
+  template <int MODE, int NPL>
+  static PMG_HD void epilogue_t(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0)
   {
     const double *O = smem + O_OFFSET;
     const int gx_end = (cx0 + BX >= p.nx) ? p.Nx : (cx0 + BX) * P;
@@ -348,14 +364,10 @@ struct PmgApplyTile {
 #pragma unroll
       for (int k = 0; k < NPL; ++k) {
         act[k] = (gz0 + k >= p.z_own_lo) && (gz0 + k < p.z_own_hi);
-        if (PREF) {
-          uc[k] = st.eu[it][k < P ? k : 0]; bb[k] = st.eb[it][k < P ? k : 0]; xo[k] = st.exo[it][k < P ? k : 0];
-        } else {
-          const int64_t g = act[k] ? g0 + k * plane : g0;
-          uc[k] = p.u[g];
-          bb[k] = (MODE != PMG_MODE_APPLY) ? p.b[g] : 0.0;
-          xo[k] = have_xold ? p.xold[g] : 0.0;
-        }
+        const int64_t g = act[k] ? g0 + k * plane : g0;
+        uc[k] = p.u[g];
+        bb[k] = (MODE != PMG_MODE_APPLY) ? p.b[g] : 0.0;
+        xo[k] = have_xold ? p.xold[g] : 0.0;
       }
       // cell-local contributions: tile-local dof coordinates are (ix + P, iy + P)
       const int tx1 = ix / P + 1, il = ix % P, ty1 = iy / P + 1, jl = iy % P;
@@ -398,14 +410,14 @@ struct PmgApplyTile {
     }
   }
 
-  template <int NPL, bool PREF>
-  static PMG_HD void phase_epilogue(const PmgApplyParams<P> &p, int tid, const ThreadState &st, const double *smem, int cx0, int cy0, int gz0)
+  template <int NPL>
+  static PMG_HD void phase_epilogue(const PmgApplyParams<P> &p, int tid, const double *smem, int cx0, int cy0, int gz0)
   {
     switch (p.mode) {
-      case PMG_MODE_APPLY: epilogue_t<PMG_MODE_APPLY, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
-      case PMG_MODE_RESIDUAL: epilogue_t<PMG_MODE_RESIDUAL, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
-      case PMG_MODE_CHEB_FIRST: epilogue_t<PMG_MODE_CHEB_FIRST, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
-      default: epilogue_t<PMG_MODE_CHEB_STEP, NPL, PREF>(p, tid, st, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_APPLY: epilogue_t<PMG_MODE_APPLY, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_RESIDUAL: epilogue_t<PMG_MODE_RESIDUAL, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      case PMG_MODE_CHEB_FIRST: epilogue_t<PMG_MODE_CHEB_FIRST, NPL>(p, tid, smem, cx0, cy0, gz0); break;
+      default: epilogue_t<PMG_MODE_CHEB_STEP, NPL>(p, tid, smem, cx0, cy0, gz0); break;
     }
   }
 
@@ -426,26 +438,34 @@ struct PmgApplyTile {
 
     ex.for_each_thread([&](int tid, ThreadState &st) { decode(tid, cx0, cy0, p, st); });
 
+    if (STAGE_IN) {
+      ex.for_each_thread([&](int tid, ThreadState &) { stage_issue(p, tid, smem, cx0, cy0, cz_first); pmg_cp_async_wait_all(); });
+      ex.sync();
+    }
     for (int cz = cz_first; cz < cz_end; ++cz) {
       const bool first = (cz == cz_first);
       const bool write_out = (cz >= cz_begin);
       ex.for_each_thread([&](int, ThreadState &st) { phase_forward(p, st, smem, cz, first); });
       ex.sync();
+      // every thread has consumed IN: start the copy of the next layer's planes; it lands during the y and
+      // backward phases and is waited for before the barrier that ends the backward phase
+      if (STAGE_IN && cz + 1 < cz_end)
+        ex.for_each_thread([&](int tid, ThreadState &) { stage_issue(p, tid, smem, cx0, cy0, cz + 1); });
       ex.for_each_thread([&](int tid, ThreadState &) { phase_y(p, tid, cx0, cy0, smem); });
       ex.sync();
       if (ALIAS) {
         ex.for_each_thread([&](int, ThreadState &st) { phase_back_read(st, smem); });
         ex.sync();
       }
-      ex.for_each_thread([&](int tid, ThreadState &st) {
+      ex.for_each_thread([&](int, ThreadState &st) {
         phase_back_write(p, st, smem, first, write_out);
-        if (PREFETCH_EPI && write_out) epilogue_prefetch(p, tid, st, cx0, cy0, cz * P);
+        if (STAGE_IN) pmg_cp_async_wait_all();
       });
       ex.sync();
       // !ALIAS: no barrier after the epilogue: the next layer's forward and y phases only touch T1, and the
       // two barriers they end with order this read of O before the next write to it
       if (write_out)
-        ex.for_each_thread([&](int tid, ThreadState &st) { phase_epilogue<P, PREFETCH_EPI>(p, tid, st, smem, cx0, cy0, cz * P); });
+        ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue<P>(p, tid, smem, cx0, cy0, cz * P); });
       if (ALIAS) ex.sync();
     }
     // top plane of the slab (owned only by the chunk that ends at the top of the mesh)
@@ -453,7 +473,7 @@ struct PmgApplyTile {
       ex.sync();
       ex.for_each_thread([&](int, ThreadState &st) { phase_flush(p, st, smem); });
       ex.sync();
-      ex.for_each_thread([&](int tid, ThreadState &st) { phase_epilogue<1, false>(p, tid, st, smem, cx0, cy0, cz_end * P); });
+      ex.for_each_thread([&](int tid, ThreadState &) { phase_epilogue<1>(p, tid, smem, cx0, cy0, cz_end * P); });
     }
   }
 };
