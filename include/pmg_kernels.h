@@ -29,9 +29,11 @@ typedef struct pmgk_level {
   double h[3];
   double S[PMGK_MAX_N1 * PMGK_MAX_N1]; /* nodal -> pencil eigenbasis, row a, column i (n1 x n1) */
   double lam[PMGK_MAX_N1];
+  double Mref[PMGK_MAX_N1 * PMGK_MAX_N1]; /* 1-D cell mass matrix of FE_Q(p) on [0,1] with QGauss(p+1) (n1 x n1) */
+  double Kref[PMGK_MAX_N1 * PMGK_MAX_N1]; /* 1-D cell stiffness matrix */
   const double *dinv_tab;  /* device, (p+2)^3 */
   const double *dinv_vec;  /* device, local vector or NULL */
-  int tile_variant;        /* tuning knob: 0 = default tile */
+  int tile_variant;        /* tuning knob: 0 = line-marching kernel (default); 2, 3 = cell-tile kernel, small/large tiles */
 } pmgk_level;
 
 enum { PMGK_APPLY = 0, PMGK_RESIDUAL = 1, PMGK_CHEB_FIRST = 2, PMGK_CHEB_STEP = 3 };

@@ -56,12 +56,15 @@ PMG_HD void pmg_cp_async_wait_all()
 #endif
 }
 
+#ifndef PMG_APPLY_MODES_DEFINED
+#define PMG_APPLY_MODES_DEFINED
 enum PmgApplyMode {
   PMG_MODE_APPLY = 0,     // out = A u
   PMG_MODE_RESIDUAL = 1,  // out = b - A u
   PMG_MODE_CHEB_FIRST = 2,// out = u + f2 * Dinv (b - A u)                       (first step of smooth())
   PMG_MODE_CHEB_STEP = 3, // out = u + f1 (u - xold) + f2 Dinv (b - A u); xold may alias out; xold==NULL => 0
 };
+#endif
 
 template <int P>
 struct PmgApplyParams {

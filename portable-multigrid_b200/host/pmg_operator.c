@@ -34,6 +34,7 @@ int pmg_laplace_operator_create(pmg_context *ctx, int dim, int degree, int nx, i
   lv->z_own_lo = op->lay.z_own_lo; lv->z_own_hi = op->lay.z_own_hi;
   lv->h[0] = 1.0 / nx; lv->h[1] = 1.0 / ny; lv->h[2] = 1.0 / nz;
   pmg_fe_fastdiag(degree, lv->S, lv->lam);
+  pmg_fe_pencil(degree, lv->Mref, lv->Kref);
   const int T = degree + 2;
   double *tab = (double *)malloc(sizeof(double) * T * T * T);
   if (!tab) { free(op); return PMG_ERR_NOMEM; }

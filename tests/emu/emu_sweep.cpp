@@ -1,0 +1,80 @@
+// tests/emu/emu_sweep.cpp -- host emulator of the line-marching apply kernel (TEST INFRASTRUCTURE).
+//
+// Compiles the product's kernel source (csrc/pmg_apply_sweep.h) for the CPU and runs every CTA's phases
+// thread by thread, so the CPU test-suite can check the kernel's index logic, halo/ownership rules and
+// fused epilogues against the oracle without a GPU.  Not part of libpmg.so: the product has no CPU path.
+#include <vector>
+#include <cstring>
+#include "pmg_apply_sweep.h"
+
+template <class Tile>
+struct SweepHostExec {
+  std::vector<typename Tile::ThreadState> st;
+  template <class F> void for_each_thread(F f) { for (int t = 0; t < Tile::NT; ++t) f(t, st[t]); }
+  void sync() {}
+};
+
+template <int P, int BX, int BY, int LZ, int NT>
+static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
+                     int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
+                     const double *u, const double *b, const double *xold, double *out, double f1, double f2,
+                     const double *dinv_vec, const double *dinv_tab)
+{
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT>;
+  PmgSweepParams<P> p;
+  std::memset(&p, 0, sizeof(p));
+  p.nx = nx; p.ny = ny; p.nz = nz;
+  p.Nx = nx * P + 1; p.Ny = ny * P + 1; p.Nz = nz * P + 1;
+  p.faces = faces; p.z0 = z0; p.nzl = nzl; p.cz_lo = cz_lo; p.cz_hi = cz_hi;
+  p.z_own_lo = z_own_lo; p.z_own_hi = z_own_hi;
+  pmg_sweep_fill_matrices<P>(p, M, K, h);
+  p.mode = mode; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
+  p.dinv_vec = dinv_vec; p.dinv_tab = dinv_tab;
+  p.tiles_x = (nx + BX - 1) / BX;
+  p.tiles_y = (ny + BY - 1) / BY;
+  const int layers = cz_hi - cz_lo;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > layers) n_chunks = layers;
+  p.layers_per_chunk = (layers + n_chunks - 1) / n_chunks;
+  p.n_chunks = (layers + p.layers_per_chunk - 1) / p.layers_per_chunk;
+  std::vector<double> smem(Tile::SMEM_DOUBLES);
+  for (int chunk = 0; chunk < p.n_chunks; ++chunk)
+    for (int ty = 0; ty < p.tiles_y; ++ty)
+      for (int tx = 0; tx < p.tiles_x; ++tx) {
+        SweepHostExec<Tile> ex;
+        ex.st.resize(Tile::NT);
+        for (auto &v : smem) v = 1e300; // poison shared memory so stale reads show up
+        Tile::run(p, ex, smem.data(), tx, ty, chunk);
+      }
+}
+
+#define ARGS nx, ny, nz, faces, z0, nzl, cz_lo, cz_hi, z_own_lo, z_own_hi, n_chunks, M, K, h, mode, u, b, xold, out, f1, f2, dinv_vec, dinv_tab
+
+// small_tiles != 0 selects deliberately tiny tiles / thread counts so that small meshes exercise many tiles,
+// several items per thread and several columns per thread; 0 = the tiles pmg_apply.cu launches
+extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, unsigned faces, int z0, int nzl,
+                         int cz_lo, int cz_hi, int z_own_lo, int z_own_hi, int n_chunks, const double *M,
+                         const double *K, const double *h, int mode, const double *u, const double *b,
+                         const double *xold, double *out, double f1, double f2, const double *dinv_vec,
+                         const double *dinv_tab)
+{
+  if (small_tiles) {
+    switch (degree) {
+      case 1: sweep_go<1, 3, 2, 3, 32>(ARGS); return 0;
+      case 2: sweep_go<2, 2, 3, 2, 32>(ARGS); return 0;
+      case 3: sweep_go<3, 2, 2, 1, 32>(ARGS); return 0;
+      case 4: sweep_go<4, 3, 2, 2, 64>(ARGS); return 0;
+      case 5: sweep_go<5, 2, 2, 1, 32>(ARGS); return 0;
+      case 6: sweep_go<6, 2, 1, 1, 32>(ARGS); return 0;
+      case 7: sweep_go<7, 1, 2, 2, 32>(ARGS); return 0;
+      case 8: sweep_go<8, 2, 2, 1, 64>(ARGS); return 0;
+    }
+    return -3;
+  }
+  switch (degree) {
+#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB) case P: sweep_go<P, BX, BY, LZ, NT>(ARGS); return 0;
+#include "pmg_apply_sweep_tiles.inc"
+#undef PMG_SWEEP_CASE
+  }
+  return -3;
+}

@@ -5,6 +5,7 @@ symbol include/*.h declares, fail loudly without a device, and its host-only hel
 oracle.  The kernels' index logic / ownership rules / fused epilogues are checked by executing the same
 source (csrc/pmg_apply_tile.h) thread by thread on the CPU (tests/emu)."""
 import ctypes as C
+import functools
 import os
 import re
 
@@ -106,7 +107,10 @@ def test_partition(pmg):
     assert pmg.host_partition(7, 1, 0) == (0, 7, True)
 
 
-# ---- the CUDA tile program under the host emulator --------------------------------------------------
+KERNELS = ["sweep", "celltile"]
+
+
+# ---- the CUDA tile programs under the host emulator --------------------------------------------------
 def _tables(emu, p, h):
     n = p + 1
     S, lam, tab = np.zeros(n * n), np.zeros(n), np.zeros((p + 2) ** 3)
@@ -115,7 +119,10 @@ def _tables(emu, p, h):
     return S, lam, tab
 
 
-def emu_apply(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, chunks=1, faces=0x3F, slab=None, dinv_vec=None, out=None):
+def emu_apply(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, chunks=1, faces=0x3F, slab=None, dinv_vec=None, out=None,
+              kernel="sweep"):
+    """Run one launch of the apply kernel under the host emulator.  kernel = "sweep" (line-marching kernel, the
+    default launch) or "celltile" (cell-tile kernel, PMG_TILE_VARIANT >= 2)."""
     nx, ny, nz = n
     h = np.array([1.0 / nx, 1.0 / ny, 1.0 / nz])
     S, lam, tab = _tables(emu, p, h)
@@ -123,8 +130,14 @@ def emu_apply(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, 
     z0, nzl, czlo, czhi, zol, zoh = (0, Nz, 0, nz, 0, Nz) if slab is None else slab
     if out is None:
         out = np.full(u.shape, np.nan)
-    rc = emu.emu_apply(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(S), P(lam), P(h), mode,
-                       P(u), P(b), P(xold), P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec), P(tab))
+    if kernel == "sweep":
+        M, K = np.zeros((p + 1) ** 2), np.zeros((p + 1) ** 2)
+        emu.pmg_fe_pencil(C.c_int(p), P(M), P(K))
+        rc = emu.emu_sweep(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(M), P(K), P(h), mode,
+                           P(u), P(b), P(xold), P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec), P(tab))
+    else:
+        rc = emu.emu_apply(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(S), P(lam), P(h), mode,
+                           P(u), P(b), P(xold), P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec), P(tab))
     assert rc == 0
     return out
 
@@ -139,18 +152,21 @@ def slab_of(p, n, cz_lo, cz_hi):
 
 @pytest.mark.parametrize("p", range(1, 9))
 @pytest.mark.parametrize("small,chunks", [(1, 1), (1, 3), (0, 2)])
-def test_emulated_apply_matches_oracle(p, small, chunks, emu, oracle):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_emulated_apply_matches_oracle(p, small, chunks, kernel, emu, oracle):
     n = (5, 4, 3) if p < 5 else (3, 2, 3)
     mf = oracle.MatrixFree(3, p, n)
     u = splitmix_src(mf.n_dofs, salt=p)
-    out = emu_apply(emu, p, n, u, small=small, chunks=chunks)
+    out = emu_apply(emu, p, n, u, small=small, chunks=chunks, kernel=kernel)
     assert not np.isnan(out).any()  # every dof is written by exactly one owner
     assert rel_l2(out, mf.vmult(u)) < 1e-13
 
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4])
-def test_emulated_epilogues_and_faces(p, emu, oracle):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_emulated_epilogues_and_faces(p, kernel, emu, oracle):
     n = (4, 3, 4)
+    emu_apply = functools.partial(globals()["emu_apply"], kernel=kernel)
     mf = oracle.MatrixFree(3, p, n)
     u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (1, 2, 3))
     Au, dinv = mf.vmult(u), mf.compute_diagonal()
@@ -172,7 +188,8 @@ def test_emulated_epilogues_and_faces(p, emu, oracle):
 
 
 @pytest.mark.parametrize("p,splits", [(1, [(0, 2), (2, 4)]), (3, [(0, 1), (1, 3), (3, 4)]), (4, [(0, 2), (2, 4)])])
-def test_emulated_slabs_cover_the_serial_result(p, splits, emu, oracle):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
     """Each rank applies the operator to its z-slab (ghost layer below, ghost plane above): the owned parts
     tile the serial result and nothing outside the owned planes is written."""
     n = (3, 4, 4)
@@ -184,7 +201,7 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, emu, oracle):
     for lo, hi in splits:
         z0, nzl, _, _, zol, zoh = sl = slab_of(p, n, lo, hi)
         ul = u[z0 * plane:(z0 + nzl) * plane].copy()
-        ol = emu_apply(emu, p, n, ul, slab=sl, chunks=2)
+        ol = emu_apply(emu, p, n, ul, slab=sl, chunks=2, kernel=kernel)
         owned = np.zeros(nzl * plane, bool)
         owned[(zol - z0) * plane:(zoh - z0) * plane] = True
         assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()

@@ -1,0 +1,80 @@
+// tools/exp/exp_sweep.cu -- stand-alone timing harness for the line-marching apply kernel (development tool).
+// Builds ONE tile configuration (-DCFG=P,BX,BY,LZ,NT -DPP=P -DMINB=n) with optional -DPMG_EXP_* switches and times
+// APPLY and CHEB_STEP launches on an n^3-cell cube:  exp_sweep <cells> [reps] [chunks]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "pmg_apply_sweep.h"
+extern "C" void pmg_fe_pencil(int p, double *M, double *K);
+#define PP C_P
+#define CFG C_P, C_BX, C_BY, C_LZ, C_NT
+#define STR2(x) #x
+#define STR(x) STR2(x)
+#define CFGSTR STR(C_P) "," STR(C_BX) "," STR(C_BY) "," STR(C_LZ) "," STR(C_NT)
+#define EXPNAME STR(C_NAME)
+#ifndef MINB
+#define MINB 3
+#endif
+using Tile = PmgSweepTile<CFG>;
+struct Ex {
+  Tile::ThreadState st;
+  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+__global__ void __launch_bounds__(Tile::NT, MINB) kern(const __grid_constant__ PmgSweepParams<PP> p)
+{
+  extern __shared__ double sm[];
+  Ex ex;
+  const int b = blockIdx.x;
+  Tile::run(p, ex, sm, b % p.tiles_x, (b / p.tiles_x) % p.tiles_y, b / (p.tiles_x * p.tiles_y));
+}
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+int main(int argc, char **argv)
+{
+  int n = argc > 1 ? atoi(argv[1]) : 0; if (n <= 0) n = (464 + PP / 2) / PP; const int reps = argc > 2 ? atoi(argv[2]) : 10;
+  int chunks = argc > 3 ? atoi(argv[3]) : 0;
+  constexpr int P = PP;
+  PmgSweepParams<P> p{};
+  p.nx = p.ny = p.nz = n; p.Nx = p.Ny = p.Nz = n * P + 1; p.faces = 0x3F;
+  p.z0 = 0; p.nzl = p.Nz; p.cz_lo = 0; p.cz_hi = n; p.z_own_lo = 0; p.z_own_hi = p.Nz;
+  constexpr int BXc = (Tile::CW - 1) / P, BYc = (Tile::RW - 1) / P;
+  p.tiles_x = (n + BXc - 1) / BXc; p.tiles_y = (n + BYc - 1) / BYc;
+  double M[100], K[100], h[3] = {1.0 / n, 1.0 / n, 1.0 / n};
+  pmg_fe_pencil(P, M, K);
+  pmg_sweep_fill_matrices<P>(p, M, K, h);
+  const size_t N = (size_t)p.Nx * p.Ny * p.Nz;
+  std::vector<double> hu(N);
+  for (size_t i = 0; i < N; ++i) hu[i] = (double)((i * 2654435761u) % 1000) / 1000.0 - 0.5;
+  double *u, *b, *xo, *out, *tab;
+  CK(cudaMalloc(&u, N * 8)); CK(cudaMalloc(&b, N * 8)); CK(cudaMalloc(&xo, N * 8)); CK(cudaMalloc(&out, N * 8));
+  CK(cudaMalloc(&tab, 1000 * 8));
+  CK(cudaMemcpy(u, hu.data(), N * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(b, hu.data(), N * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(xo, 0, N * 8)); CK(cudaMemset(tab, 0, 8000));
+  p.u = u; p.b = b; p.xold = xo; p.out = out; p.f1 = 0.3; p.f2 = 0.1; p.dinv_tab = tab; p.dinv_vec = nullptr;
+  const int smem = Tile::SMEM_DOUBLES * 8;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Tile::NT, smem));
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+  if (chunks <= 0) { // waves * (layers + 1 + 1/P) minimal
+    const int slots = 148 * per_sm, tiles = p.tiles_x * p.tiles_y; double best = -1;
+    for (int c = 1; c <= n; ++c) { int lpc = (n + c - 1) / c; if ((n + lpc - 1) / lpc != c) continue;
+      long waves = ((long)tiles * c + slots - 1) / slots; double cost = waves * (lpc + (c > 1 ? 1.0 + 1.0 / P : 0.0));
+      if (best < 0 || cost < best) { best = cost; chunks = c; } }
+  }
+  p.layers_per_chunk = (n + chunks - 1) / chunks; p.n_chunks = (n + p.layers_per_chunk - 1) / p.layers_per_chunk;
+  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int mode : {0, 3}) {
+    p.mode = mode; p.out = (mode == 3) ? xo : out;
+    for (int i = 0; i < 3; ++i) kern<<<grid, Tile::NT, smem>>>(p);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) kern<<<grid, Tile::NT, smem>>>(p);
+    cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    printf("%s P=%d n=%d N=%zu cfg=%s minb=%d regs=%d smem=%dKB ctas/sm=%d grid=%d chunks=%d mode=%d: %.3f ms %.1f GDoF/s\n",
+           EXPNAME, P, n, N, CFGSTR, MINB, fa.numRegs, smem / 1024, per_sm, grid, p.n_chunks, mode, ms, N / ms / 1e6);
+  }
+  return 0;
+}
