@@ -98,13 +98,13 @@ __global__ void __launch_bounds__(NT, MINB)
 pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p)
 {
   using Tile = PmgSweepTile<P, BX, BY, LZ, NT>;
-  extern __shared__ double pmg_smem[];
+  extern __shared__ __align__(128) double pmg_sweep_smem[];
   PmgSweepDeviceExec<Tile> ex;
   const int b = blockIdx.x;
   const int tile_x = b % p.tiles_x;
   const int tile_y = (b / p.tiles_x) % p.tiles_y;
   const int chunk = b / (p.tiles_x * p.tiles_y);
-  Tile::run(p, ex, pmg_smem, tile_x, tile_y, chunk);
+  Tile::run(p, ex, pmg_sweep_smem, tile_x, tile_y, chunk);
 }
 
 // number of z-chunks: minimise waves * (layers + recomputed layer and plane below the chunk)
@@ -138,22 +138,29 @@ static int launch_sweep(const pmgk_level *lv, int mode, const double *u, const d
   p.z_own_lo = lv->z_own_lo; p.z_own_hi = lv->z_own_hi;
   p.tiles_x = (lv->nx + BX - 1) / BX;
   p.tiles_y = (lv->ny + BY - 1) / BY;
-  const int smem_bytes = Tile::SMEM_DOUBLES * (int)sizeof(double);
+  // APPLY stages only u; the other modes also stage the epilogue's b / x_old rows
+  const int epi = (mode != PMGK_APPLY);
+  const int smem_bytes = Tile::smem_doubles(epi != 0) * (int)sizeof(double);
   static int configured = 0;
-  static int ctas_per_sm = 1;
+  static int ctas_per_sm[2] = {1, 1};
   if (!configured) {
-    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB>, NT, smem_bytes));
-    if (ctas_per_sm < 1) return PMG_ERR_CUDA;
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Tile::SMEM_DOUBLES * (int)sizeof(double)));
+    for (int e = 0; e < 2; ++e) {
+      PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[e], pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB>, NT,
+                                                                   Tile::smem_doubles(e != 0) * sizeof(double)));
+      if (ctas_per_sm[e] < 1) return PMG_ERR_CUDA;
+    }
     configured = 1;
   }
-  const int slots = pmgk_device_sm_count() * ctas_per_sm;
+  const int slots = pmgk_device_sm_count() * ctas_per_sm[epi];
   choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, &p.n_chunks, &p.layers_per_chunk);
   pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
   p.mode = mode; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
   const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
   if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
+  if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
   pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB><<<grid, NT, smem_bytes, stream>>>(p);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);

@@ -19,14 +19,23 @@
 //    of the vertex DoF shared with the next cell in a register: complete results, no cross-thread sums, no
 //    atomics, and the halo a CTA recomputes for its neighbours shrinks to one partial cell per line.
 //  * CTA = BX x BY cell columns, marching through cell layers in z, LZ layers (LZ P dof planes) per step:
-//      stage    the u planes of the NEXT step are copied global -> shared with cp.async (LDGSTS) while this step
-//               computes (two staging buffers), so no sweep ever waits on HBM latency
-//      phase 1  thread = (x, plane): marches in y, in place in the staging buffer: u -> c, and d -> second buffer
+//      stage    every input stream reaches shared memory through the bulk async copy engine (cp.async.bulk, SASS
+//               UBLKCP, completion on an mbarrier): one instruction per tile row, issued a full step ahead for u (two
+//               staging buffers) and two phases ahead for the epilogue's b and x_old rows; no thread spends registers on
+//               loads.  The engine wants 16-byte aligned rows while dof rows start at any 8-byte address (odd row
+//               lengths): a row is fetched from the aligned address below it and read back through a one-element shift
+//               that depends on the row.  (2-D TMA tensor tiles -- one instruction per plane -- would be the better fit,
+//               but UTMALDG raises "illegal instruction" on this pool's B200s even for the CUDA programming guide's
+//               reference example: tools/exp/tma_test2.cu.)
+//      phase 1  thread = (x, plane): marches in y: u (staging buffer, left intact) -> c, d
 //      phase 2  thread = (y, plane): marches in x, in place: (c, d) -> (g, m)
 //      phase 3  thread = dof column (x, y): z sweep over the layer's P+1 planes -- the values of the plane shared
 //               with the layer below and its partial sum stay in registers (3 doubles per column) -- and the
-//               epilogue (Dirichlet identity / residual / Chebyshev update) before the single coalesced store.
-//    Every shared-memory access is conflict-free (odd row pitch, lanes along x or along y).
+//               epilogue (Dirichlet identity / residual / Chebyshev update; u, b, x_old from shared memory) before
+//               the single coalesced store.
+//    Every shared-memory access is conflict-free (odd row pitch of the work buffers, lanes along x or along y).
+//  * Vectors must be 16-byte aligned with 16 readable bytes after their last element (the library's allocator
+//    provides both).
 //  * The 1-D matrices are symmetric and centro-symmetric: the kernel addresses them through the canonical
 //    representative of each entry, so a phase needs only ~(p+1)^2/2 distinct constants, which stay in uniform
 //    registers instead of being re-fetched for every FMA.
@@ -55,32 +64,55 @@ enum PmgApplyMode {
 };
 #endif
 
-// 8-byte asynchronous global -> shared copy (LDGSTS); a plain copy under the host emulator
-PMG_HD void pmg_sweep_cp_async8(double *dst_smem, const double *src_global)
+// ---- bulk async copy engine + mbarrier (sm_90+ PTX; plain copies / no-ops under the host emulator, which runs the
+// issuing loops of all threads to completion before any consumer) -----------------------------------------------------
+PMG_HD void pmg_mbar_init(uint64_t *bar, int count)
 {
 #if defined(__CUDA_ARCH__)
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_global) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 #else
-  *dst_smem = *src_global;
+  (void)bar; (void)count;
 #endif
 }
-PMG_HD void pmg_sweep_cp_async_wait_all()
+PMG_HD void pmg_mbar_init_fence()
 {
 #if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 #endif
 }
-
-// hint: bring the 128-byte lines covering [ptr, ptr + bytes) into L1; nothing under the host emulator
-PMG_HD void pmg_sweep_prefetch_l1(const double *ptr, int bytes)
+// one arrival that also announces `bytes` of bulk copies completing on the barrier
+PMG_HD void pmg_mbar_arrive_expect(uint64_t *bar, int bytes)
 {
 #if defined(__CUDA_ARCH__)
-  const unsigned long long a = (unsigned long long)ptr;
-  for (unsigned long long l = a & ~127ull; l < a + (unsigned)bytes; l += 128)
-    asm volatile("prefetch.global.L1 [%0];\n" ::"l"(l) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 #else
-  (void)ptr; (void)bytes;
+  (void)bar; (void)bytes;
+#endif
+}
+PMG_HD void pmg_mbar_wait(uint64_t *bar, int parity)
+{
+#if defined(__CUDA_ARCH__)
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+#else
+  (void)bar; (void)parity;
+#endif
+}
+// copy `bytes` (multiple of 16) from 16-byte aligned global memory to 16-byte aligned shared memory
+PMG_HD void pmg_bulk_copy(double *dst_smem, const double *src_global, int bytes, uint64_t *bar)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_global), "r"(bytes),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+#else
+  (void)bar;
+  for (int i = 0; i < bytes / 8; ++i) dst_smem[i] = src_global[i];
 #endif
 }
 
@@ -152,15 +184,27 @@ struct PmgSweepTile {
   static constexpr int N1 = P + 1;
   static constexpr int NT = NT_;
   static constexpr int NPS = LZ * P;          // dof planes per step
-  static constexpr int XW = (BX + 1) * P + 1; // x points of the tile buffers: global x = (cx0-1) P + xl
-  static constexpr int XP = XW | 1;           // odd row pitch: the column walks of phase 2 are conflict-free
-  static constexpr int YW = (BY + 1) * P + 1; // rows of the staging buffer A: global y = (cy0-1) P + yl
-  static constexpr int RW = BY * P + 1;       // rows of buffer B:            global y = cy0 P + r
+  static constexpr int XW = (BX + 1) * P + 1; // x points of the tile: global x = (cx0-1) P + xl
+  static constexpr int YW = (BY + 1) * P + 1; // rows of the u tile:   global y = (cy0-1) P + yl
+  static constexpr int RW = BY * P + 1;       // owned rows:           global y = cy0 P + r
   static constexpr int CW = BX * P + 1;       // owned dof columns in x (the +1 only at the mesh end)
-  static constexpr int APLANE = YW * XP, BPLANE = RW * XP;
-  static constexpr int ABUF = NPS * APLANE;   // one staging buffer: u, then c, then g (in place)
-  static constexpr int B_OFFSET = 2 * ABUF;   // buffer B: d, then m
-  static constexpr int SMEM_DOUBLES = 2 * ABUF + NPS * BPLANE;
+  // staging buffers (bulk-copy targets): a row is fetched from the 16-byte aligned address at or below its first
+  // element, so it holds one extra element and its pitch is even; element x of row (k, y) is at [x + shift(k, y)]
+  static constexpr int XPA = (XW | 1) + 1;    // elements per copied u row = pitch of A
+  static constexpr int XPE = (CW | 1) + 1;    // elements per copied b / x_old row = pitch of E
+  static constexpr int APLANE = YW * XPA, EPLANE = RW * XPE;
+  static constexpr int ABUF = NPS * APLANE;   // one u staging buffer
+  static constexpr int EBUF = NPS * EPLANE;   // one epilogue array (b or x_old)
+  // work buffers C (c, then g) and D (d, then m): odd pitch, the column walks of phase 2 are conflict-free
+  static constexpr int XP = XW | 1;
+  static constexpr int CPLANE = RW * XP;
+  static constexpr int CBUF = (NPS * CPLANE + 15) & ~15;
+  static constexpr int C_OFFSET = 2 * ABUF, D_OFFSET = C_OFFSET + CBUF;
+  static constexpr int E_OFFSET = D_OFFSET + CBUF; // b boxes, then x_old boxes (not allocated for APPLY)
+  static constexpr int BAR_OFFSET_APPLY = E_OFFSET, BAR_OFFSET_EPI = E_OFFSET + 2 * EBUF;
+  static constexpr int NBAR = 3;              // mbarriers: u buffer 0, u buffer 1, E
+  static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return (epilogue_inputs ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
+  static constexpr int SMEM_DOUBLES = BAR_OFFSET_EPI + NBAR;
   static constexpr int NITEM1 = XW * NPS;
   static constexpr int IT2 = (RW * NPS + NT - 1) / NT; // phase-2 items per thread
   static constexpr int NCOL = (CW * RW + NT - 1) / NT; // dof columns per thread in phase 3
@@ -174,6 +218,8 @@ struct PmgSweepTile {
   struct ThreadState {
     double carry[NCOL]; // z-sweep sum of the plane shared with the next cell layer, per owned dof column
     double gP[NCOL], mP[NCOL]; // (g, m) of that plane
+    double uP[NCOL];    // u of that plane (epilogue input of the next layer's plane 0)
+    double dinv[NCOL][P]; // inverse diagonal of the column's planes k = 0..P-1 of an interior layer (CHEB modes, table)
     int info[NCOL];     // ox | oy << 8 | Dirichlet-in-xy << 16 | x position type << 20 | y position type << 24; -1 = none
     int item2[IT2];     // phase-2 item: row | plane << 16; -1 = none
   };
@@ -183,6 +229,10 @@ struct PmgSweepTile {
     int ncx, ncy;     // valid owned cells
     int x_end, y_end; // tile touches the high end of the mesh (owns the last vertex line)
     int cw, rows;     // owned dof columns / rows
+    int nxodd, plodd; // parities of Nx and of Nx * Ny: how the row shift changes from row to row / plane to plane
+    int64_t eA, eE;   // element index (local vector) of tile point (xl=0, yl=0) resp. (ox=0, oy=0) in local plane 0
+    int64_t n_local;  // elements of the local vector
+    bool has_e, has_xo; // the mode reads b / x_old
   };
 
   static PMG_HD TileGeom geom(const PmgSweepParams<P> &p, int tile_x, int tile_y)
@@ -195,23 +245,39 @@ struct PmgSweepTile {
     t.y_end = (t.cy0 + t.ncy == p.ny);
     t.cw = t.ncx * P + t.x_end;
     t.rows = t.ncy * P + t.y_end;
+    t.nxodd = p.Nx & 1; t.plodd = (p.Nx & 1) & (p.Ny & 1);
+    t.eA = (int64_t)((t.cy0 - 1) * P) * p.Nx + (t.cx0 - 1) * P;
+    t.eE = (int64_t)(t.cy0 * P) * p.Nx + t.cx0 * P;
+    t.n_local = (int64_t)p.Nx * p.Ny * p.nzl;
+    t.has_e = (p.mode != PMG_MODE_APPLY);
+    t.has_xo = (p.mode == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
     return t;
   }
 
+  // shift of the tile row that starts at element e of the vector (e may be negative: two's complement keeps parity)
+  static PMG_HD int shift_of(int64_t e) { return (int)(e & 1); }
+
   static PMG_HD void decode(const PmgSweepParams<P> &p, const TileGeom &t, int tid, ThreadState &st)
   {
+    constexpr int T = P + 2;
     const int ncols = t.cw * t.rows;
 #pragma unroll
     for (int ci = 0; ci < NCOL; ++ci) {
       const int col = tid + ci * NT;
-      st.carry[ci] = 0.0; st.gP[ci] = 0.0; st.mP[ci] = 0.0;
+      st.carry[ci] = 0.0; st.gP[ci] = 0.0; st.mP[ci] = 0.0; st.uP[ci] = 0.0;
+#pragma unroll
+      for (int k = 0; k < P; ++k) st.dinv[ci][k] = 1.0;
       if (col < ncols) {
         const int oy = col / t.cw, ox = col - oy * t.cw;
         const int gx = t.cx0 * P + ox, gy = t.cy0 * P + oy;
         const int dirxy = (gx == 0 && (p.faces & 1u)) || (gx == p.Nx - 1 && (p.faces >> 1 & 1u)) ||
                           (gy == 0 && (p.faces >> 2 & 1u)) || (gy == p.Ny - 1 && (p.faces >> 3 & 1u));
-        st.info[ci] = ox | (oy << 8) | (dirxy << 16) | (pmg_sweep_pos_type<P>(gx, p.Nx) << 20) |
-                      (pmg_sweep_pos_type<P>(gy, p.Ny) << 24);
+        const int tx = pmg_sweep_pos_type<P>(gx, p.Nx), ty = pmg_sweep_pos_type<P>(gy, p.Ny);
+        st.info[ci] = ox | (oy << 8) | (dirxy << 16) | (tx << 20) | (ty << 24);
+        if (p.mode >= PMG_MODE_CHEB_FIRST && !p.dinv_vec && !dirxy) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) st.dinv[ci][k] = p.dinv_tab[tx + T * ty + T * T * k];
+        }
       } else {
         st.info[ci] = -1;
       }
@@ -224,43 +290,54 @@ struct PmgSweepTile {
     }
   }
 
-  // ---- stage: copy `npl` dof planes gz0 .. of the tile's (XW x YW) footprint into staging buffer A ------------
-  // lane = x point (coalesced), warp w takes rows w, w + NW, ...: two pointer increments per copy
-  static PMG_HD void stage(const PmgSweepParams<P> &p, const TileGeom &t, int tid, double *A, int gz0, int npl)
+  // ---- stage: one bulk copy per tile row.  Every thread issues its share and arrives once on the barrier ---------
+  // copy `nelem` (even) elements around vector elements [e, e + nelem - 1) to the 16-byte aligned row `dst`
+  static PMG_HD int issue_row(const double *vec, int64_t e, int nelem, int64_t n_local, double *dst, uint64_t *bar)
   {
-#ifdef PMG_EXP_NOSTAGE
-    return;
-#endif
-    constexpr int NW = NT / 32;
-    const int64_t plane = (int64_t)p.Nx * p.Ny;
-    const int gx0 = (t.cx0 - 1) * P, gy0 = (t.cy0 - 1) * P;
-    const int yl_lo = (t.cy0 == 0) ? P : 0; // rows below the mesh do not exist
-    const int yl_hi = (t.ncy + 1) * P;      // last row the sweeps read
-    const int64_t row_step = (int64_t)NW * p.Nx;
-#pragma unroll
-    for (int xl = tid % 32; xl < XW; xl += 32) {
-      const int gx = gx0 + xl;
-      if (gx < 0 || gx >= p.Nx) continue;
-      const int yl0 = yl_lo + tid / 32;
-      const double *src0 = p.u + (int64_t)(gz0 - p.z0) * plane + (int64_t)(gy0 + yl0) * p.Nx + gx;
-      double *dst0 = A + yl0 * XP + xl;
-#pragma unroll
-      for (int k = 0; k < NPS; ++k) {
-        if (k < npl) {
-          const double *src = src0 + k * plane;
-          double *dst = dst0 + k * APLANE;
-#pragma unroll 4
-          for (int yl = yl0; yl <= yl_hi; yl += NW) {
-            pmg_sweep_cp_async8(dst, src);
-            src += row_step; dst += NW * XP;
-          }
-        }
-      }
+    int64_t lo = e - shift_of(e);          // 16-byte aligned start (even element index)
+    if (lo < 0) {                          // below the vector: only points x < 0 of the first row, never read
+      const int sk = (int)(-lo);
+      lo += sk; dst += sk; nelem -= sk;
     }
+    if (lo + nelem > n_local + 2)          // beyond the vector's 16 bytes of padding: only x > Nx-1 of the last row
+      nelem = (int)((n_local + 2 - lo) & ~(int64_t)1);
+    if (nelem <= 0) return 0;
+    pmg_bulk_copy(dst, vec + lo, nelem * 8, bar);
+    return nelem * 8;
   }
 
-  // ---- phase 1: y sweep in place.  item = (xl, k): column xl of plane k; u -> c in A, d -> B ------------------
-  static PMG_HD void phase1(const PmgSweepParams<P> &p, const TileGeom &t, int tid, double *A, double *B, int gz0, int npl)
+  // u planes gz0 .. gz0+npl-1 (tile footprint XW x YW) -> A
+  static PMG_HD void stage_u(const PmgSweepParams<P> &p, const TileGeom &t, int tid, double *A, uint64_t *bar, int gz0, int npl)
+  {
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const int yl_lo = (t.cy0 == 0) ? P : 0;   // rows below the mesh do not exist
+    const int nrow = (t.ncy + 1) * P + 1 - yl_lo;
+    int bytes = 0;
+    for (int i = tid; i < npl * nrow; i += NT) {
+      const int k = i / nrow, yl = yl_lo + (i - k * nrow);
+      bytes += issue_row(p.u, t.eA + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)yl * p.Nx, XPA, t.n_local,
+                         A + k * APLANE + yl * XPA, bar);
+    }
+    pmg_mbar_arrive_expect(bar, bytes);
+  }
+
+  // b (and x_old) rows of the owned columns of output planes gz0 .. gz0+npl-1 -> E
+  static PMG_HD void stage_e(const PmgSweepParams<P> &p, const TileGeom &t, int tid, double *E, uint64_t *bar, int gz0, int npl)
+  {
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    int bytes = 0;
+    for (int i = tid; i < npl * t.rows; i += NT) {
+      const int k = i / t.rows, r = i - k * t.rows;
+      const int64_t e = t.eE + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)r * p.Nx;
+      bytes += issue_row(p.b, e, XPE, t.n_local, E + k * EPLANE + r * XPE, bar);
+      if (t.has_xo) bytes += issue_row(p.xold, e, XPE, t.n_local, E + EBUF + k * EPLANE + r * XPE, bar);
+    }
+    pmg_mbar_arrive_expect(bar, bytes);
+  }
+
+  // ---- phase 1: y sweep.  item = (xl, k): column xl of plane k of A (u, read only) -> c in C, d in D -------------
+  static PMG_HD void phase1(const PmgSweepParams<P> &p, const TileGeom &t, int tid, const double *A, double *Cb, double *Db,
+                            int gz0, int npl)
   {
     const bool dir_lo = (p.faces >> 2 & 1u), dir_hi = (p.faces >> 3 & 1u);
     for (int item = tid; item < NITEM1; item += NT) {
@@ -269,30 +346,35 @@ struct PmgSweepTile {
       const int gx = (t.cx0 - 1) * P + xl;
       if (gx < 0 || gx >= p.Nx) continue;
       const int gz = gz0 + k;
-      double *Ac = A + k * APLANE + xl;       // row yl of the column: Ac[yl * XP]; owned row r is yl = r + P
-      double *Bc = B + k * BPLANE + xl;       // row r: Bc[r * XP]
+      double *Cc = Cb + k * CPLANE + xl;       // row r: Cc[r * XP]
+      double *Dc = Db + k * CPLANE + xl;
       const bool zero_line = (gx == 0 && (p.faces & 1u)) || (gx == p.Nx - 1 && (p.faces >> 1 & 1u)) ||
                              (gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u));
       if (zero_line) { // Dirichlet values read as 0 (:250-254): the whole line of c, d vanishes
-        for (int r = 0; r < t.rows; ++r) { Ac[(r + P) * XP] = 0.0; Bc[r * XP] = 0.0; }
+        for (int r = 0; r < t.rows; ++r) { Cc[r * XP] = 0.0; Dc[r * XP] = 0.0; }
         continue;
       }
+      // row yl of the column is at Ae[yl * XPA] for even yl and Ao[yl * XPA] for odd yl (the row shift alternates
+      // from row to row when Nx is odd)
+      const int s0 = shift_of(t.eA + (int64_t)(gz - p.z0) * p.Nx * p.Ny);
+      const double *Ae = A + k * APLANE + xl + s0;
+      const double *Ao = A + k * APLANE + xl + (s0 ^ t.nxodd);
+#define PMG_AROW(yl) ((((yl) & 1) ? Ao : Ae)[(yl) * XPA])
       double cc = 0.0, cd = 0.0, v0;
       if (t.cy0 > 0) { // partial cell below the tile: only its contribution to the first owned row
         double v[N1];
 #pragma unroll
-        for (int j = 0; j < N1; ++j) v[j] = Ac[j * XP];
+        for (int j = 0; j < N1; ++j) v[j] = PMG_AROW(j);
         if (t.cy0 == 1 && dir_lo) v[0] = 0.0;
 #pragma unroll
         for (int j = 0; j < N1; ++j) { cc = fma(PMG_M(P, j), v[j], cc); cd = fma(PMG_KY(P, j), v[j], cd); }
         v0 = v[P];
       } else {
-        v0 = dir_lo ? 0.0 : Ac[P * XP];
+        v0 = dir_lo ? 0.0 : PMG_AROW(P);
       }
 #pragma unroll
       for (int c = 0; c < BY; ++c) {
         if (c < t.ncy) {
-          double *Acc = Ac + (P + c * P) * XP;
           double vj = v0;
           double sc[N1], sd[N1];
 #pragma unroll
@@ -300,7 +382,7 @@ struct PmgSweepTile {
           sc[0] = cc; sd[0] = cd;
 #pragma unroll
           for (int j = 0; j < N1; ++j) {
-            if (j > 0) vj = Acc[j * XP];
+            if (j > 0) vj = PMG_AROW(P + c * P + j);
             if (j == P && dir_hi && t.cy0 + c == p.ny - 1) vj = 0.0;
 #pragma unroll
             for (int kk = 0; kk < N1; ++kk) {
@@ -309,35 +391,26 @@ struct PmgSweepTile {
             }
           }
 #pragma unroll
-          for (int kk = 0; kk < P; ++kk) { Acc[kk * XP] = sc[kk]; Bc[(c * P + kk) * XP] = sd[kk]; }
+          for (int kk = 0; kk < P; ++kk) { Cc[(c * P + kk) * XP] = sc[kk]; Dc[(c * P + kk) * XP] = sd[kk]; }
           cc = sc[P]; cd = sd[P]; v0 = vj;
         }
       }
-      if (t.y_end) { Ac[(P + t.ncy * P) * XP] = cc; Bc[t.ncy * P * XP] = cd; }
+      if (t.y_end) { Cc[t.ncy * P * XP] = cc; Dc[t.ncy * P * XP] = cd; }
+#undef PMG_AROW
     }
   }
 
   // ---- phase 2: x sweep in place.  item = (row r, plane k): (c, d) -> (g, m) ---------------------------------
-  // gz_pf >= 0: the item also asks L1 for its row of the epilogue's inputs (b, xold) in plane gz_pf + k, i.e. of the NEXT
-  // step's output planes, so that phase 3 finds them in L1
-  static PMG_HD void phase2(const PmgSweepParams<P> &p, const TileGeom &t, const ThreadState &st, double *A, double *B, int npl,
-                            int gz_pf)
+  static PMG_HD void phase2(const PmgSweepParams<P> &p, const TileGeom &t, const ThreadState &st, double *Cb, double *Db, int npl)
   {
 #pragma unroll
     for (int it = 0; it < IT2; ++it) {
       const int item = st.item2[it];
       if (item < 0) continue;
       const int r = item & 0xFFFF, k = item >> 16;
-      if (gz_pf >= 0 && p.mode != PMG_MODE_APPLY && gz_pf + k < p.z_own_hi) {
-        const int64_t g = ((int64_t)(gz_pf + k - p.z0) * p.Ny + (t.cy0 * P + r)) * p.Nx + t.cx0 * P;
-        // (measured on B200, Q4: L1 line prefetch 2.6 -> 1.9 ms per fused step; a bulk L2 prefetch gave nothing)
-        pmg_sweep_prefetch_l1(p.b + g, t.cw * 8);
-        pmg_sweep_prefetch_l1(p.u + g, t.cw * 8);
-        if (p.mode == PMG_MODE_CHEB_STEP && p.xold) pmg_sweep_prefetch_l1(p.xold + g, t.cw * 8);
-      }
       if (k >= npl) continue;
-      double *Cr = A + k * APLANE + (r + P) * XP;
-      double *Dr = B + k * BPLANE + r * XP;
+      double *Cr = Cb + k * CPLANE + r * XP;
+      double *Dr = Db + k * CPLANE + r * XP;
       double cg = 0.0, cm = 0.0, c0, d0;
       if (t.cx0 > 0) { // partial cell left of the tile: only its contribution to the first owned column
         double c[N1], d[N1];
@@ -379,87 +452,55 @@ struct PmgSweepTile {
     }
   }
 
-  // inputs of the epilogue for the P planes of one dof column of one layer
-  struct EpiIn { double u[P], b[P], xo[P]; };
-
-  // issue the global loads of the epilogue of planes gz0 .. gz0+P-1 of one column (nothing in APPLY mode: Dirichlet rows
-  // in x/y are written by fixup_dirichlet_xy, Dirichlet planes in z by the rare branch of epi_store)
   template <int MODE>
-  static PMG_HD void epi_load(const PmgSweepParams<P> &p, int64_t g0, int64_t plane, int gz0, EpiIn &in)
+  static PMG_HD double epi_value(const PmgSweepParams<P> &p, double y, double uc, double bb, double xo, bool dir, double dinv)
   {
-    if (MODE != PMG_MODE_APPLY) {
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        const int gz = gz0 + k;
-        const bool act = (gz >= p.z_own_lo && gz < p.z_own_hi);
-        const int64_t g = act ? g0 + k * plane : g0; // any valid address: the value is not used
-        in.u[k] = p.u[g];
-        in.b[k] = p.b[g];
-        if (MODE == PMG_MODE_CHEB_STEP) in.xo[k] = p.xold ? p.xold[g] : 0.0;
-      }
-    }
+    const double Au = dir ? uc : y; // Dirichlet rows are the identity (:718)
+    if (MODE == PMG_MODE_APPLY) return Au;
+    if (MODE == PMG_MODE_RESIDUAL) return bb - Au;
+    const double corr = p.f2 * (dir ? 1.0 : dinv) * (bb - Au);
+    if (MODE == PMG_MODE_CHEB_FIRST) return uc + corr;
+    return uc + p.f1 * (uc - xo) + corr;
   }
 
-  template <int MODE>
-  static PMG_HD void epi_store(const PmgSweepParams<P> &p, int64_t g, double y, double uc, double bb, double xo, bool dirxy,
-                               bool dirz, int tab_index)
-  {
-    if (MODE == PMG_MODE_APPLY) {
-      if (dirz) p.out[g] = p.u[g];       // Dirichlet rows are the identity (:718); first and last plane only
-      else if (!dirxy) p.out[g] = y;     // (Dirichlet rows in x/y: fixup_dirichlet_xy)
-      return;
-    }
-    const bool dir = dirxy || dirz;
-    const double Au = dir ? uc : y;
-    double r;
-    if (MODE == PMG_MODE_RESIDUAL) {
-      r = bb - Au;
-    } else {
-      double dinv;
-      if (dir) dinv = 1.0;
-      else if (p.dinv_vec) dinv = p.dinv_vec[g];
-      else dinv = p.dinv_tab[tab_index];
-      const double corr = p.f2 * dinv * (bb - Au);
-      if (MODE == PMG_MODE_CHEB_FIRST) r = uc + corr;
-      else r = uc + p.f1 * (uc - xo) + corr;
-    }
-    p.out[g] = r;
-  }
-
-  // ---- phase 3: z sweep + epilogue for the `nlay` cell layers cz0 .. of the step; thread = NCOL dof columns -----
-  // FULL: every plane of the layer is owned, written and not a Dirichlet plane (all layers but the first and last of the
-  // mesh / slab / halo): straight-line code.  The epilogue's global loads of column i+1 are issued before column i is
-  // computed.
+  // ---- phase 3: z sweep + epilogue of cell layer cz = layer l of the step; thread = NCOL dof columns --------------
+  // All inputs are in shared memory: g, m in C, D; u in A (planes q = l P + k of the step: plane q - 1 of A holds dof plane
+  // cz0 P + q, q >= 1; dof plane cz0 P itself is kept in a register from the previous step); b, x_old in E (plane q).
+  // FULL: every plane of the layer is owned, written, inside the mesh's first/last planes: straight-line code.
   template <int MODE, bool FULL>
-  static PMG_HD void phase3_layer(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *B,
-                                  int l, int cz, bool write)
+  static PMG_HD void phase3_layer(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *Cb,
+                                  const double *Db, const double *E, int l, int cz0, bool write)
   {
     constexpr int T = P + 2;
+    const int cz = cz0 + l;
     const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const bool has_xo = (MODE == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
     const int64_t glayer = (int64_t)(t.cy0 * P) * p.Nx + t.cx0 * P + ((int64_t)cz * P - p.z0) * plane;
-    EpiIn in[2];
-    auto col_g0 = [&](int ci) { const int info = st.info[ci]; return glayer + (int64_t)((info >> 8) & 0xFF) * p.Nx + (info & 0xFF); };
-    if (write && st.info[0] >= 0) epi_load<MODE>(p, col_g0(0), plane, cz * P, in[0]);
+    const int64_t zoff = (int64_t)(cz0 * P - p.z0) * plane;
 #pragma unroll
     for (int ci = 0; ci < NCOL; ++ci) {
-      if (write && ci + 1 < NCOL && st.info[ci + 1] >= 0) epi_load<MODE>(p, col_g0(ci + 1), plane, cz * P, in[(ci + 1) & 1]);
       const int info = st.info[ci];
       if (info < 0) continue;
       const int ox = info & 0xFF, oy = (info >> 8) & 0xFF;
-      const double *G = A + (oy + P) * XP + P + ox;
-      const double *Mm = B + oy * XP + P + ox;
+      const double *G = Cb + oy * XP + P + ox;
+      const double *Mm = Db + oy * XP + P + ox;
       double g[N1], m[N1];
       g[0] = st.gP[ci]; m[0] = st.mP[ci];
 #pragma unroll
-      for (int kp = 1; kp < N1; ++kp) { g[kp] = G[(l * P + kp - 1) * APLANE]; m[kp] = Mm[(l * P + kp - 1) * BPLANE]; }
+      for (int kp = 1; kp < N1; ++kp) { g[kp] = G[(l * P + kp - 1) * CPLANE]; m[kp] = Mm[(l * P + kp - 1) * CPLANE]; }
       double top = 0.0; // row P: the partial sum of the plane shared with the next layer
 #pragma unroll
       for (int kp = 0; kp < N1; ++kp) top = fma(PMG_MZ(P, kp), g[kp], fma(PMG_KZ(P, kp), m[kp], top));
+      // shifts of this column's rows in dof plane cz0 P; plane cz0 P + q has them flipped for odd q when Nx Ny is odd
+      const int sa = shift_of(t.eA + zoff + (int64_t)(oy + P) * p.Nx), se = shift_of(t.eE + zoff + (int64_t)oy * p.Nx);
+      const double *Uc = A + (oy + P) * XPA + P + ox;
+      const double *Ec = E + oy * XPE + ox;
+      const int qt = l * P + P;          // the layer's top plane
+      const double utop = Uc[(qt - 1) * APLANE + (sa ^ ((qt & 1) & t.plodd))];
       if (write) {
         const bool dirxy = (info >> 16) & 1;
         const int tbase = ((info >> 20) & 0xF) + T * ((info >> 24) & 0xF);
-        const int64_t g0 = col_g0(ci);
-        const EpiIn &e = in[ci & 1];
+        double *po = p.out + glayer + (int64_t)oy * p.Nx + ox;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           const int gz = cz * P + k;
@@ -467,19 +508,29 @@ struct PmgSweepTile {
             double y = (k == 0) ? st.carry[ci] : 0.0;
 #pragma unroll
             for (int kp = 0; kp < N1; ++kp) y = fma(PMG_MZ(k, kp), g[kp], fma(PMG_KZ(k, kp), m[kp], y));
-            const bool dirz = FULL ? false : ((gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u)));
-            const int ztype = FULL ? k : pmg_sweep_pos_type<P>(gz, p.Nz);
-            epi_store<MODE>(p, g0 + k * plane, y, e.u[k], e.b[k], e.xo[k], dirxy, dirz, tbase + T * T * ztype);
+            const bool dir = dirxy || (!FULL && ((gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u))));
+            const int q = l * P + k;
+            const int fl = (q & 1) & t.plodd;
+            double uc = 0.0, bb = 0.0, xo = 0.0, dinv = 1.0;
+            if (MODE != PMG_MODE_APPLY || dir) uc = (q == 0) ? st.uP[ci] : Uc[(q - 1) * APLANE + (sa ^ fl)];
+            if (MODE != PMG_MODE_APPLY) bb = Ec[q * EPLANE + (se ^ fl)];
+            if (has_xo) xo = Ec[EBUF + q * EPLANE + (se ^ fl)];
+            if (MODE >= PMG_MODE_CHEB_FIRST) {
+              if (p.dinv_vec) dinv = p.dinv_vec[glayer + (int64_t)oy * p.Nx + ox + k * plane];
+              else if (FULL) dinv = st.dinv[ci][k];
+              else dinv = p.dinv_tab[tbase + T * T * pmg_sweep_pos_type<P>(gz, p.Nz)];
+            }
+            po[k * plane] = epi_value<MODE>(p, y, uc, bb, xo, dir, dinv);
           }
         }
       }
-      st.carry[ci] = top; st.gP[ci] = g[P]; st.mP[ci] = m[P];
+      st.carry[ci] = top; st.gP[ci] = g[P]; st.mP[ci] = m[P]; st.uP[ci] = utop;
     }
   }
 
   template <int MODE>
-  static PMG_HD void phase3_t(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *B,
-                              int cz0, int nlay, int cz_write)
+  static PMG_HD void phase3_t(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *Cb,
+                              const double *Db, const double *E, int cz0, int nlay, int cz_write)
   {
 #pragma unroll
     for (int l = 0; l < LZ; ++l) {
@@ -488,37 +539,40 @@ struct PmgSweepTile {
         const bool write = (cz >= cz_write);
         // plane 0 of the mesh (Dirichlet or not, its inverse-diagonal type differs) takes the general path
         const bool full = write && cz > 0 && cz * P >= p.z_own_lo && cz * P + P <= p.z_own_hi;
-        if (full) phase3_layer<MODE, true>(p, t, st, A, B, l, cz, true);
-        else phase3_layer<MODE, false>(p, t, st, A, B, l, cz, write);
+        if (full) phase3_layer<MODE, true>(p, t, st, A, Cb, Db, E, l, cz0, true);
+        else phase3_layer<MODE, false>(p, t, st, A, Cb, Db, E, l, cz0, write);
       }
     }
   }
 
-  static PMG_HD void phase3(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *B,
-                            int cz0, int nlay, int cz_write)
+  static PMG_HD void phase3(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *Cb,
+                            const double *Db, const double *E, int cz0, int nlay, int cz_write)
   {
     switch (p.mode) {
-      case PMG_MODE_APPLY: phase3_t<PMG_MODE_APPLY>(p, t, st, A, B, cz0, nlay, cz_write); break;
-      case PMG_MODE_RESIDUAL: phase3_t<PMG_MODE_RESIDUAL>(p, t, st, A, B, cz0, nlay, cz_write); break;
-      case PMG_MODE_CHEB_FIRST: phase3_t<PMG_MODE_CHEB_FIRST>(p, t, st, A, B, cz0, nlay, cz_write); break;
-      default: phase3_t<PMG_MODE_CHEB_STEP>(p, t, st, A, B, cz0, nlay, cz_write); break;
+      case PMG_MODE_APPLY: phase3_t<PMG_MODE_APPLY>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
+      case PMG_MODE_RESIDUAL: phase3_t<PMG_MODE_RESIDUAL>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
+      case PMG_MODE_CHEB_FIRST: phase3_t<PMG_MODE_CHEB_FIRST>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
+      default: phase3_t<PMG_MODE_CHEB_STEP>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
     }
   }
 
-  // after the prologue: (g, m) of the first layer's plane 0 into the registers
-  static PMG_HD void phase3_init(ThreadState &st, const double *A, const double *B)
+  // after the prologue: (g, m, u) of the first layer's plane 0 (dof plane gz, in plane slot 0 of A0) into the registers
+  static PMG_HD void phase3_init(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A0, const double *Cb,
+                                 const double *Db, int gz)
   {
+    const int64_t zoff = (int64_t)(gz - p.z0) * p.Nx * p.Ny;
 #pragma unroll
     for (int ci = 0; ci < NCOL; ++ci) {
       const int info = st.info[ci];
       if (info < 0) continue;
       const int ox = info & 0xFF, oy = (info >> 8) & 0xFF;
-      st.gP[ci] = A[(oy + P) * XP + P + ox];
-      st.mP[ci] = B[oy * XP + P + ox];
+      st.gP[ci] = Cb[oy * XP + P + ox];
+      st.mP[ci] = Db[oy * XP + P + ox];
+      st.uP[ci] = A0[(oy + P) * XPA + P + ox + shift_of(t.eA + zoff + (int64_t)(oy + P) * p.Nx)];
     }
   }
 
-  // the mesh's top plane: the carried sums are complete (no cell layer above)
+  // the mesh's top plane: the carried sums are complete (no cell layer above); a single plane, inputs read from global
   template <int MODE>
   static PMG_HD void flush_t(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, int gz)
   {
@@ -531,33 +585,15 @@ struct PmgSweepTile {
       if (info < 0) continue;
       const int ox = info & 0xFF, oy = (info >> 8) & 0xFF;
       const int64_t g = (int64_t)(gz - p.z0) * plane + (int64_t)(t.cy0 * P + oy) * p.Nx + t.cx0 * P + ox;
-      double uc = 0.0, bb = 0.0, xo = 0.0;
-      if (MODE != PMG_MODE_APPLY) { uc = p.u[g]; bb = p.b[g]; }
+      const bool dir = dirz || ((info >> 16) & 1);
+      double uc = 0.0, bb = 0.0, xo = 0.0, dinv = 1.0;
+      if (MODE != PMG_MODE_APPLY || dir) uc = p.u[g];
+      if (MODE != PMG_MODE_APPLY) bb = p.b[g];
       if (MODE == PMG_MODE_CHEB_STEP && p.xold) xo = p.xold[g];
-      epi_store<MODE>(p, g, st.carry[ci], uc, bb, xo, (info >> 16) & 1, dirz,
-                      ((info >> 20) & 0xF) + T * ((info >> 24) & 0xF) + T * T * pmg_sweep_pos_type<P>(gz, p.Nz));
-    }
-  }
-
-  // APPLY mode: Dirichlet rows in x / y are the identity (:718).  Their lines are copied u -> out here, after the march,
-  // for planes [pz_lo, pz_hi): many independent loads in flight instead of one dependent load per store in the epilogue.
-  static PMG_HD void fixup_dirichlet_xy(const PmgSweepParams<P> &p, const TileGeom &t, int tid, int pz_lo, int pz_hi)
-  {
-    const int npz = pz_hi - pz_lo;
-    if (npz <= 0) return;
-    const int64_t plane = (int64_t)p.Nx * p.Ny;
-    const int64_t base = (int64_t)(pz_lo - p.z0) * plane + (int64_t)(t.cy0 * P) * p.Nx + t.cx0 * P;
-    for (int side = 0; side < 4; ++side) {
-      int len; int64_t first, step;
-      if (side == 0) { if (!(t.cy0 == 0 && (p.faces >> 2 & 1u))) continue; len = t.cw; first = 0; step = 1; }
-      else if (side == 1) { if (!(t.y_end && (p.faces >> 3 & 1u))) continue; len = t.cw; first = (int64_t)(t.rows - 1) * p.Nx; step = 1; }
-      else if (side == 2) { if (!(t.cx0 == 0 && (p.faces & 1u))) continue; len = t.rows; first = 0; step = p.Nx; }
-      else { if (!(t.x_end && (p.faces >> 1 & 1u))) continue; len = t.rows; first = t.cw - 1; step = p.Nx; }
-      for (int idx = tid; idx < len * npz; idx += NT) {
-        const int pz = idx / len, i = idx - pz * len;
-        const int64_t g = base + pz * plane + first + i * step;
-        p.out[g] = p.u[g];
-      }
+      if (MODE >= PMG_MODE_CHEB_FIRST)
+        dinv = p.dinv_vec ? p.dinv_vec[g]
+                          : p.dinv_tab[((info >> 20) & 0xF) + T * ((info >> 24) & 0xF) + T * T * pmg_sweep_pos_type<P>(gz, p.Nz)];
+      p.out[g] = epi_value<MODE>(p, st.carry[ci], uc, bb, xo, dir, dinv);
     }
   }
 
@@ -573,6 +609,7 @@ struct PmgSweepTile {
 
   // ---- the tile program -----------------------------------------------------
   // Exec provides: template<F> void for_each_thread(F f)  with f(int tid, ThreadState&);  void sync()
+  // smem must be 16-byte aligned.
   template <class Exec>
   static PMG_HD void run(const PmgSweepParams<P> &p, Exec &ex, double *smem, int tile_x, int tile_y, int chunk)
   {
@@ -584,58 +621,64 @@ struct PmgSweepTile {
     // the layer below the chunk is recomputed when its planes are stored locally (they are unless it is outside the mesh)
     const bool halo = (cz_begin > 0) && ((cz_begin - 1) * P >= p.z0);
     const int cz_first = halo ? cz_begin - 1 : cz_begin;
-    double *B = smem + B_OFFSET;
+    double *Cb = smem + C_OFFSET, *Db = smem + D_OFFSET, *E = smem + E_OFFSET;
+    uint64_t *bars = (uint64_t *)(smem + (t.has_e ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY));
+    int par_u[2] = {0, 0}, par_e = 0; // phase parity each barrier completes next
 
-    // prologue: plane 0 of the first layer through the y and x sweeps; meanwhile the first step's planes arrive
-    int cur = 1;
-    ex.for_each_thread([&](int tid, ThreadState &st) {
-      int n1 = cz_end - cz_first; if (n1 > LZ) n1 = LZ;
-      stage(p, t, tid, smem, cz_first * P, 1);
-      stage(p, t, tid, smem + ABUF, cz_first * P + 1, n1 * P);
-      decode(p, t, tid, st);
-      pmg_sweep_cp_async_wait_all();
+    // prologue: plane 0 of the first layer -> buffer 0; the first step's planes -> buffer 1, its b / x_old rows -> E
+    int n0 = cz_end - cz_first; if (n0 > LZ) n0 = LZ;
+    ex.for_each_thread([&](int tid, ThreadState &) {
+      if (tid == 0) {
+        for (int i = 0; i < NBAR; ++i) pmg_mbar_init(bars + i, NT);
+        pmg_mbar_init_fence();
+      }
     });
     ex.sync();
-    ex.for_each_thread([&](int tid, ThreadState &) { phase1(p, t, tid, smem, B, cz_first * P, 1); });
+    ex.for_each_thread([&](int tid, ThreadState &) {
+      stage_u(p, t, tid, smem, bars + 0, cz_first * P, 1);
+      stage_u(p, t, tid, smem + ABUF, bars + 1, cz_first * P + 1, n0 * P);
+      if (t.has_e) stage_e(p, t, tid, E, bars + 2, cz_first * P, n0 * P);
+    });
+    ex.for_each_thread([&](int tid, ThreadState &st) {
+      decode(p, t, tid, st);
+      pmg_mbar_wait(bars + 0, par_u[0]);
+      phase1(p, t, tid, smem, Cb, Db, cz_first * P, 1);
+    });
+    par_u[0] ^= 1;
     ex.sync();
-    ex.for_each_thread([&](int, ThreadState &st) { phase2(p, t, st, smem, B, 1, -1); });
+    ex.for_each_thread([&](int, ThreadState &st) { phase2(p, t, st, Cb, Db, 1); });
     ex.sync();
-    ex.for_each_thread([&](int, ThreadState &st) { phase3_init(st, smem, B); });
+    ex.for_each_thread([&](int, ThreadState &st) { phase3_init(p, t, st, smem, Cb, Db, cz_first * P); });
     ex.sync();
 
+    int cur = 1;
     for (int cz = cz_first; cz < cz_end; cz += LZ) {
       double *A = smem + cur * ABUF;
       int nlay = cz_end - cz; if (nlay > LZ) nlay = LZ;
       int nnext = cz_end - (cz + LZ); if (nnext > LZ) nnext = LZ;
-      // the next step's u planes land in the other staging buffer while this step computes
-      if (nnext > 0)
-        ex.for_each_thread([&](int tid, ThreadState &) { stage(p, t, tid, smem + (cur ^ 1) * ABUF, (cz + LZ) * P + 1, nnext * P); });
-#ifndef PMG_EXP_NOP1
-      ex.for_each_thread([&](int tid, ThreadState &) { phase1(p, t, tid, A, B, cz * P + 1, nlay * P); });
-#endif
+      ex.for_each_thread([&](int tid, ThreadState &) {
+        // the other staging buffer and E were last read before the barrier that ended the previous step: fetch the next
+        // step's u planes (a full step ahead) and this step's b / x_old rows (two phases ahead)
+        if (nnext > 0) stage_u(p, t, tid, smem + (cur ^ 1) * ABUF, bars + (cur ^ 1), (cz + LZ) * P + 1, nnext * P);
+        if (t.has_e && cz > cz_first) stage_e(p, t, tid, E, bars + 2, cz * P, nlay * P);
+        pmg_mbar_wait(bars + cur, par_u[cur]);
+        phase1(p, t, tid, A, Cb, Db, cz * P + 1, nlay * P);
+      });
+      par_u[cur] ^= 1;
       ex.sync();
-#ifndef PMG_EXP_NOP2
-      ex.for_each_thread([&](int, ThreadState &st) { phase2(p, t, st, A, B, nlay * P, (nnext > 0) ? (cz + LZ) * P : -1); });
-#endif
+      ex.for_each_thread([&](int, ThreadState &st) { phase2(p, t, st, Cb, Db, nlay * P); });
       ex.sync();
       ex.for_each_thread([&](int, ThreadState &st) {
-#ifndef PMG_EXP_NOP3
-        phase3(p, t, st, A, B, cz, nlay, cz_begin);
-#endif
-        pmg_sweep_cp_async_wait_all();
+        if (t.has_e) pmg_mbar_wait(bars + 2, par_e);
+        phase3(p, t, st, A, Cb, Db, E, cz, nlay, cz_begin);
       });
+      par_e ^= 1;
       ex.sync();
       cur ^= 1;
     }
     // top plane of the mesh (owned by the chunk that ends there)
-    const bool top = (cz_end == p.cz_hi && cz_end * P < p.z_own_hi);
-    if (top) ex.for_each_thread([&](int, ThreadState &st) { flush(p, t, st, cz_end * P); });
-    if (p.mode == PMG_MODE_APPLY) {
-      int pz_lo = cz_begin * P, pz_hi = cz_end * P + (top ? 1 : 0);
-      if (pz_lo < p.z_own_lo) pz_lo = p.z_own_lo;
-      if (pz_hi > p.z_own_hi) pz_hi = p.z_own_hi;
-      ex.for_each_thread([&](int tid, ThreadState &) { fixup_dirichlet_xy(p, t, tid, pz_lo, pz_hi); });
-    }
+    if (cz_end == p.cz_hi && cz_end * P < p.z_own_hi)
+      ex.for_each_thread([&](int, ThreadState &st) { flush(p, t, st, cz_end * P); });
   }
 #undef PMG_M
 #undef PMG_KX

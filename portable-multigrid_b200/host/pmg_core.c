@@ -192,7 +192,8 @@ int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector
   if (!v) return PMG_ERR_NOMEM;
   v->ctx = ctx; v->lay = *lay;
   if (lay->n_local > 0) {
-    if (cudaMalloc((void **)&v->d, sizeof(double) * (size_t)lay->n_local) != cudaSuccess) {
+    /* + 16 bytes: the apply kernel's bulk row copies fetch whole 16-byte granules (csrc/pmg_apply_sweep.h) */
+    if (cudaMalloc((void **)&v->d, sizeof(double) * ((size_t)lay->n_local + 2)) != cudaSuccess) {
       pmg_set_error("cudaMalloc of %lld doubles failed", (long long)lay->n_local);
       free(v);
       return PMG_ERR_NOMEM;

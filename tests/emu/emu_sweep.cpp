@@ -28,7 +28,19 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
   p.faces = faces; p.z0 = z0; p.nzl = nzl; p.cz_lo = cz_lo; p.cz_hi = cz_hi;
   p.z_own_lo = z_own_lo; p.z_own_hi = z_own_hi;
   pmg_sweep_fill_matrices<P>(p, M, K, h);
-  p.mode = mode; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
+  // the kernel's bulk row copies may read 16 bytes past the last element: run on padded copies (x_old may alias out)
+  const size_t n_local = (size_t)p.Nx * p.Ny * nzl;
+  std::vector<double> up(u, u + n_local), bp, xp;
+  const size_t pad = (size_t)p.Nx + 2;
+  up.resize(n_local + pad, 0.0);
+  if (b) { bp.assign(b, b + n_local); bp.resize(n_local + pad, 0.0); }
+  const bool alias = (xold != nullptr && xold == out);
+  std::vector<double> outp;
+  if (alias) { outp.assign(xold, xold + n_local); outp.resize(n_local + pad, 0.0); }
+  else if (xold) { xp.assign(xold, xold + n_local); xp.resize(n_local + pad, 0.0); }
+  p.mode = mode; p.u = up.data(); p.b = b ? bp.data() : nullptr;
+  p.xold = alias ? outp.data() : (xold ? xp.data() : nullptr);
+  p.out = alias ? outp.data() : out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = dinv_vec; p.dinv_tab = dinv_tab;
   p.tiles_x = (nx + BX - 1) / BX;
   p.tiles_y = (ny + BY - 1) / BY;
@@ -37,7 +49,7 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
   if (n_chunks > layers) n_chunks = layers;
   p.layers_per_chunk = (layers + n_chunks - 1) / n_chunks;
   p.n_chunks = (layers + p.layers_per_chunk - 1) / p.layers_per_chunk;
-  std::vector<double> smem(Tile::SMEM_DOUBLES);
+  std::vector<double> smem(Tile::SMEM_DOUBLES + 16);
   for (int chunk = 0; chunk < p.n_chunks; ++chunk)
     for (int ty = 0; ty < p.tiles_y; ++ty)
       for (int tx = 0; tx < p.tiles_x; ++tx) {
@@ -46,6 +58,7 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
         for (auto &v : smem) v = 1e300; // poison shared memory so stale reads show up
         Tile::run(p, ex, smem.data(), tx, ty, chunk);
       }
+  if (alias) std::memcpy(out, outp.data(), n_local * sizeof(double));
 }
 
 #define ARGS nx, ny, nz, faces, z0, nzl, cz_lo, cz_hi, z_own_lo, z_own_hi, n_chunks, M, K, h, mode, u, b, xold, out, f1, f2, dinv_vec, dinv_tab

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include "pmg_apply_sweep.h"
 extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #define PP C_P
@@ -24,7 +25,7 @@ struct Ex {
 };
 __global__ void __launch_bounds__(Tile::NT, MINB) kern(const __grid_constant__ PmgSweepParams<PP> p)
 {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(128) double sm[];
   Ex ex;
   const int b = blockIdx.x;
   Tile::run(p, ex, sm, b % p.tiles_x, (b / p.tiles_x) % p.tiles_y, b / (p.tiles_x * p.tiles_y));
@@ -47,12 +48,12 @@ int main(int argc, char **argv)
   std::vector<double> hu(N);
   for (size_t i = 0; i < N; ++i) hu[i] = (double)((i * 2654435761u) % 1000) / 1000.0 - 0.5;
   double *u, *b, *xo, *out, *tab;
-  CK(cudaMalloc(&u, N * 8)); CK(cudaMalloc(&b, N * 8)); CK(cudaMalloc(&xo, N * 8)); CK(cudaMalloc(&out, N * 8));
+  CK(cudaMalloc(&u, N * 8 + 8 * (size_t)p.Nx + 16)); CK(cudaMalloc(&b, N * 8 + 8 * (size_t)p.Nx + 16)); CK(cudaMalloc(&xo, N * 8 + 8 * (size_t)p.Nx + 16)); CK(cudaMalloc(&out, N * 8 + 8 * (size_t)p.Nx + 16));
   CK(cudaMalloc(&tab, 1000 * 8));
   CK(cudaMemcpy(u, hu.data(), N * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(b, hu.data(), N * 8, cudaMemcpyHostToDevice));
   CK(cudaMemset(xo, 0, N * 8)); CK(cudaMemset(tab, 0, 8000));
   p.u = u; p.b = b; p.xold = xo; p.out = out; p.f1 = 0.3; p.f2 = 0.1; p.dinv_tab = tab; p.dinv_vec = nullptr;
-  const int smem = Tile::SMEM_DOUBLES * 8;
+  int smem = Tile::SMEM_DOUBLES * 8;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Tile::NT, smem));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
@@ -67,6 +68,8 @@ int main(int argc, char **argv)
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int mode : {0, 3}) {
     p.mode = mode; p.out = (mode == 3) ? xo : out;
+    smem = Tile::smem_doubles(mode != 0) * 8;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Tile::NT, smem));
     for (int i = 0; i < 3; ++i) kern<<<grid, Tile::NT, smem>>>(p);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
