@@ -3,7 +3,7 @@
  *
  * Mirrors Portable::LaplaceOperator<dim,fe_degree,number>
  * (reference include/operators/portable_laplace_operator.h:383-461) method by method; the
- * cell loop itself is csrc/pmg_apply_tile.h.  The constructor replaces MatrixFree::reinit +
+ * cell loop itself is csrc/pmg_apply_sweep.h.  The constructor replaces MatrixFree::reinit +
  * setup_dirichlet_boundary_dofs_masks (:463-555): on the structured box nothing needs to be
  * stored per cell, only the 1-D tables.
  */
