@@ -38,29 +38,47 @@ __device__ __forceinline__ bool on_dirichlet(int gx, int gy, int gz, int Nx, int
          (gy == Ny - 1 && (faces >> 3 & 1u)) || (gz == 0 && (faces >> 4 & 1u)) || (gz == Nz - 1 && (faces >> 5 & 1u));
 }
 
-// one CTA handles CPB consecutive coarse cells (x fastest)
-template <int CPB>
+// cell coordinates of the CTA's cells, decoded once per CTA (64-bit divisions) into shared memory
+__device__ __forceinline__ void decode_cells(const XferGeom &g, int64_t cell0, int64_t ncells, int cpb, int *cc)
+{
+  for (int c = threadIdx.x; c < cpb; c += blockDim.x) {
+    const int64_t cell = cell0 + c;
+    if (cell < ncells) {
+      cc[3 * c] = (int)(cell % g.ncx);
+      cc[3 * c + 1] = (int)((cell / g.ncx) % g.ncy);
+      cc[3 * c + 2] = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
+    } else {
+      cc[3 * c] = -1; cc[3 * c + 1] = 0; cc[3 * c + 2] = 0;
+    }
+  }
+}
+
+// one CTA handles CPB consecutive coarse cells (x fastest).  TNC, TNF: compile-time 1-D sizes (0 = read them from g):
+// the contractions unroll and the index arithmetic becomes multiply-shift
+template <int CPB, int TNC, int TNF>
 __global__ void __launch_bounds__(256) k_prolongate(const XferGeom g, const double *__restrict__ P1d, double *dst, const double *__restrict__ src)
 {
   extern __shared__ double sm[];
-  const int NC = g.NC, NF = g.NF;
+  const int NC = TNC ? TNC : g.NC, NF = TNF ? TNF : g.NF;
   const int nvc = NC * NC * NC, nt1 = NC * NC * NF, nt2 = NC * NF * NF;
   double *sP = sm;                       // NC*NF
   double *vc = sP + NC * NF;             // CPB * nvc
   double *t1 = vc + CPB * nvc;           // CPB * nt1
   double *t2 = t1 + CPB * nt1;           // CPB * nt2
+  int *cc = (int *)(t2 + CPB * nt2);     // 3 * CPB cell coordinates
   const int tid = threadIdx.x, nth = blockDim.x;
   const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
   const int64_t cell0 = (int64_t)blockIdx.x * CPB;
 
   for (int i = tid; i < NC * NF; i += nth) sP[i] = P1d[i];
+  decode_cells(g, cell0, ncells, CPB, cc);
+  __syncthreads();
   // gather coarse cell values
   for (int w = tid; w < CPB * nvc; w += nth) {
     const int c = w / nvc, i = w % nvc;
-    const int64_t cell = cell0 + c;
     double v = 0.0;
-    if (cell < ncells) {
-      const int cx = (int)(cell % g.ncx), cy = (int)((cell / g.ncx) % g.ncy), cz = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
+    const int cx = cc[3 * c], cy = cc[3 * c + 1], cz = cc[3 * c + 2];
+    if (cx >= 0) {
       const int ix = i % NC, iy = (i / NC) % NC, iz = i / (NC * NC);
       const int gx = cx * g.pc + ix, gy = cy * g.pc + iy, gz = cz * g.pc + iz;
       // h: constrained coarse dofs read as 0 (dof_indices_coarse == invalid, :170-173);
@@ -77,6 +95,7 @@ __global__ void __launch_bounds__(256) k_prolongate(const XferGeom g, const doub
     const int xf = r % NF, zy = r / NF;
     const double *in = vc + c * nvc + zy * NC;
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < NC; ++k) s += sP[k * NF + xf] * in[k];
     t1[w] = s;
   }
@@ -87,6 +106,7 @@ __global__ void __launch_bounds__(256) k_prolongate(const XferGeom g, const doub
     const int xf = r % NF, yf = (r / NF) % NF, z = r / (NF * NF);
     const double *in = t1 + c * nt1 + z * NC * NF + xf;
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < NC; ++k) s += sP[k * NF + yf] * in[k * NF];
     t2[w] = s;
   }
@@ -95,43 +115,45 @@ __global__ void __launch_bounds__(256) k_prolongate(const XferGeom g, const doub
   const int nf3 = NF * NF * NF;
   for (int w = tid; w < CPB * nf3; w += nth) {
     const int c = w / nf3, r = w % nf3;
-    const int64_t cell = cell0 + c;
-    if (cell >= ncells) continue;
+    const int cx = cc[3 * c], cy = cc[3 * c + 1], cz = cc[3 * c + 2];
+    if (cx < 0) continue;
     const int xf = r % NF, yf = (r / NF) % NF, zf = r / (NF * NF);
-    const int cx = (int)(cell % g.ncx), cy = (int)((cell / g.ncx) % g.ncy), cz = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
     if ((xf == NF - 1 && cx != g.ncx - 1) || (yf == NF - 1 && cy != g.ncy - 1) || (zf == NF - 1 && cz != g.ncz - 1)) continue;
     const int gx = cx * g.fstep + xf, gy = cy * g.fstep + yf, gz = cz * g.fstep + zf;
     if (gz < g.f_zown_lo || gz >= g.f_zown_hi) continue;
     if (on_dirichlet(gx, gy, gz, g.Nfx, g.Nfy, g.Nfz, g.faces)) continue; // weight 0 / masked (:1346-1349, p :306-324)
     const double *in = t2 + c * nt2 + yf * NF + xf;
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < NC; ++k) s += sP[k * NF + zf] * in[k * NF * NF];
     dst[((int64_t)(gz - g.f_z0) * g.Nfy + gy) * g.Nfx + gx] += s;
   }
 }
 
 // pass 1 of the restriction: cell-local (P^T x P^T x P^T) applied to the patch's owned fine dofs
-template <int CPB>
+template <int CPB, int TNC, int TNF>
 __global__ void __launch_bounds__(256) k_restrict_cells(const XferGeom g, const double *__restrict__ P1d, double *scratch, const double *__restrict__ src)
 {
   extern __shared__ double sm[];
-  const int NC = g.NC, NF = g.NF;
+  const int NC = TNC ? TNC : g.NC, NF = TNF ? TNF : g.NF;
   const int nf3 = NF * NF * NF, nt1 = NC * NF * NF, nt2 = NC * NC * NF, nvc = NC * NC * NC;
   double *sP = sm;                 // NC*NF
   double *vf = sP + NC * NF;       // CPB*nf3
   double *t1 = vf + CPB * nf3;     // CPB*nt1   [zc][yf][xf]
   double *t2 = t1 + CPB * nt1;     // CPB*nt2   [zc][yc][xf]
+  int *cc = (int *)(t2 + CPB * nt2);
   const int tid = threadIdx.x, nth = blockDim.x;
   const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
   const int64_t cell0 = (int64_t)blockIdx.x * CPB;
   for (int i = tid; i < NC * NF; i += nth) sP[i] = P1d[i];
+  decode_cells(g, cell0, ncells, CPB, cc);
+  __syncthreads();
   for (int w = tid; w < CPB * nf3; w += nth) {
     const int c = w / nf3, r = w % nf3;
-    const int64_t cell = cell0 + c;
     double v = 0.0;
-    if (cell < ncells) {
+    const int cx = cc[3 * c], cy = cc[3 * c + 1], cz = cc[3 * c + 2];
+    if (cx >= 0) {
       const int xf = r % NF, yf = (r / NF) % NF, zf = r / (NF * NF);
-      const int cx = (int)(cell % g.ncx), cy = (int)((cell / g.ncx) % g.ncy), cz = g.ccz_lo + (int)(cell / ((int64_t)g.ncx * g.ncy));
       const bool owned = !((xf == NF - 1 && cx != g.ncx - 1) || (yf == NF - 1 && cy != g.ncy - 1) || (zf == NF - 1 && cz != g.ncz - 1));
       const int gx = cx * g.fstep + xf, gy = cy * g.fstep + yf, gz = cz * g.fstep + zf;
       if (owned && !on_dirichlet(gx, gy, gz, g.Nfx, g.Nfy, g.Nfz, g.faces))
@@ -146,6 +168,7 @@ __global__ void __launch_bounds__(256) k_restrict_cells(const XferGeom g, const 
     const int xy = r % (NF * NF), zc = r / (NF * NF);
     const double *in = vf + c * nf3 + xy;
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < NF; ++k) s += sP[zc * NF + k] * in[k * NF * NF];
     t1[w] = s;
   }
@@ -156,6 +179,7 @@ __global__ void __launch_bounds__(256) k_restrict_cells(const XferGeom g, const 
     const int xf = r % NF, yc = (r / NF) % NC, zc = r / (NF * NC);
     const double *in = t1 + c * nt1 + zc * NF * NF + xf;
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < NF; ++k) s += sP[yc * NF + k] * in[k * NF];
     t2[w] = s;
   }
@@ -163,13 +187,13 @@ __global__ void __launch_bounds__(256) k_restrict_cells(const XferGeom g, const 
   // x: scratch[cell][zc][yc][xc]
   for (int w = tid; w < CPB * nvc; w += nth) {
     const int c = w / nvc, r = w % nvc;
-    const int64_t cell = cell0 + c;
-    if (cell >= ncells) continue;
+    if (cc[3 * c] < 0) continue;
     const int xc = r % NC, zy = r / NC;
     const double *in = t2 + c * nt2 + zy * NF;
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < NF; ++k) s += sP[xc * NF + k] * in[k];
-    scratch[cell * nvc + r] = s;
+    scratch[(cell0 + c) * nvc + r] = s;
   }
 }
 
@@ -248,30 +272,58 @@ extern "C" int64_t pmgk_restrict_scratch_doubles(int kind, const pmgk_level *coa
   return (int64_t)coarse->nx * coarse->ny * (coarse->cz_hi - coarse->cz_lo) * NC * NC * NC;
 }
 
-template <int CPB>
+template <int CPB, int TNC, int TNF>
 static int launch_prolongate(const XferGeom &g, const double *P1d, double *dst, const double *src, cudaStream_t s)
 {
   const int NC = g.NC, NF = g.NF;
-  const size_t smem = sizeof(double) * (NC * NF + CPB * (NC * NC * NC + NC * NC * NF + NC * NF * NF));
+  const size_t smem = sizeof(double) * (NC * NF + CPB * (NC * NC * NC + NC * NC * NF + NC * NF * NF)) + sizeof(int) * 3 * CPB;
   const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
-  if (smem > 48 * 1024) PMG_CUDA_CHECK(cudaFuncSetAttribute(k_prolongate<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_prolongate<CPB><<<(unsigned)((ncells + CPB - 1) / CPB), 256, smem, s>>>(g, P1d, dst, src);
+  if (smem > 48 * 1024) PMG_CUDA_CHECK(cudaFuncSetAttribute(k_prolongate<CPB, TNC, TNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_prolongate<CPB, TNC, TNF><<<(unsigned)((ncells + CPB - 1) / CPB), 256, smem, s>>>(g, P1d, dst, src);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
 }
 
-template <int CPB>
+template <int CPB, int TNC, int TNF>
 static int launch_restrict(const XferGeom &g, const double *P1d, double *scratch, const double *src, cudaStream_t s)
 {
   const int NC = g.NC, NF = g.NF;
-  const size_t smem = sizeof(double) * (NC * NF + CPB * (NF * NF * NF + NC * NF * NF + NC * NC * NF));
+  const size_t smem = sizeof(double) * (NC * NF + CPB * (NF * NF * NF + NC * NF * NF + NC * NC * NF)) + sizeof(int) * 3 * CPB;
   const int64_t ncells = (int64_t)g.ncx * g.ncy * (g.ccz_hi - g.ccz_lo);
-  if (smem > 48 * 1024) PMG_CUDA_CHECK(cudaFuncSetAttribute(k_restrict_cells<CPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_restrict_cells<CPB><<<(unsigned)((ncells + CPB - 1) / CPB), 256, smem, s>>>(g, P1d, scratch, src);
+  if (smem > 48 * 1024) PMG_CUDA_CHECK(cudaFuncSetAttribute(k_restrict_cells<CPB, TNC, TNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_restrict_cells<CPB, TNC, TNF><<<(unsigned)((ncells + CPB - 1) / CPB), 256, smem, s>>>(g, P1d, scratch, src);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
+}
+
+// the (NC, NF) pairs of the drivers' hierarchies get compile-time sizes: h-transfer of Q1..Q4 and the p-transfers
+// p -> p/2 (Q2->Q1 and Q4->Q2 share their sizes with the h-transfers of Q1 and Q2); everything else runs the generic code
+#define PMG_XFER_DISPATCH(LAUNCH, ...)                                                        \
+  do {                                                                                        \
+    const int cpb = pick_cpb(g.NC, g.NF);                                                     \
+    if (g.NC == 2 && g.NF == 3 && cpb == 8) return LAUNCH<8, 2, 3>(__VA_ARGS__);              \
+    if (g.NC == 3 && g.NF == 5 && cpb == 8) return LAUNCH<8, 3, 5>(__VA_ARGS__);              \
+    if (g.NC == 2 && g.NF == 4 && cpb == 8) return LAUNCH<8, 2, 4>(__VA_ARGS__);              \
+    if (g.NC == 4 && g.NF == 7 && cpb == 4) return LAUNCH<4, 4, 7>(__VA_ARGS__);              \
+    if (g.NC == 5 && g.NF == 9 && cpb == 2) return LAUNCH<2, 5, 9>(__VA_ARGS__);              \
+    switch (cpb) {                                                                            \
+      case 8: return LAUNCH<8, 0, 0>(__VA_ARGS__);                                            \
+      case 4: return LAUNCH<4, 0, 0>(__VA_ARGS__);                                            \
+      case 2: return LAUNCH<2, 0, 0>(__VA_ARGS__);                                            \
+      default: return LAUNCH<1, 0, 0>(__VA_ARGS__);                                           \
+    }                                                                                         \
+  } while (0)
+
+static int dispatch_prolongate(const XferGeom &g, const double *P1d, double *dst, const double *src, cudaStream_t s)
+{
+  PMG_XFER_DISPATCH(launch_prolongate, g, P1d, dst, src, s);
+}
+
+static int dispatch_restrict(const XferGeom &g, const double *P1d, double *scratch, const double *src, cudaStream_t s)
+{
+  PMG_XFER_DISPATCH(launch_restrict, g, P1d, scratch, src, s);
 }
 
 extern "C" int pmgk_prolongate_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
@@ -281,12 +333,7 @@ extern "C" int pmgk_prolongate_and_add(int kind, const pmgk_level *coarse, const
   const int rc = make_geom(kind, coarse, fine, &g);
   if (rc) return rc;
   if (g.ccz_hi <= g.ccz_lo) return 0;
-  switch (pick_cpb(g.NC, g.NF)) {
-    case 8: return launch_prolongate<8>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
-    case 4: return launch_prolongate<4>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
-    case 2: return launch_prolongate<2>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
-    default: return launch_prolongate<1>(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
-  }
+  return dispatch_prolongate(g, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
 }
 
 extern "C" int pmgk_restrict_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
@@ -296,12 +343,7 @@ extern "C" int pmgk_restrict_and_add(int kind, const pmgk_level *coarse, const p
   int rc = make_geom(kind, coarse, fine, &g);
   if (rc) return rc;
   if (g.ccz_hi <= g.ccz_lo) return 0;
-  switch (pick_cpb(g.NC, g.NF)) {
-    case 8: rc = launch_restrict<8>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
-    case 4: rc = launch_restrict<4>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
-    case 2: rc = launch_restrict<2>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
-    default: rc = launch_restrict<1>(g, P1d, scratch, src_fine, (cudaStream_t)stream); break;
-  }
+  rc = dispatch_restrict(g, P1d, scratch, src_fine, (cudaStream_t)stream);
   if (rc) return rc;
   const int64_t total = (int64_t)g.Ncx * g.Ncy * ((g.ccz_hi - g.ccz_lo) * g.pc + 1);
   int64_t nb = (total + 255) / 256;
