@@ -93,11 +93,11 @@ struct PmgSweepDeviceExec {
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-template <int P, int BX, int BY, int LZ, int NT, int MINB>
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US>
 __global__ void __launch_bounds__(NT, MINB)
 pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US>;
   extern __shared__ __align__(128) double pmg_sweep_smem[];
   PmgSweepDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -124,11 +124,11 @@ static void choose_sweep_chunks(int tiles, int layers, int slots, int degree, in
   *layers_per_chunk = (layers + best_c - 1) / best_c;
 }
 
-template <int P, int BX, int BY, int LZ, int NT, int MINB>
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US>
 static int launch_sweep(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                         double *out, double f1, double f2, cudaStream_t stream, int *geom)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
   p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
@@ -144,10 +144,10 @@ static int launch_sweep(const pmgk_level *lv, int mode, const double *u, const d
   static int configured = 0;
   static int ctas_per_sm[2] = {1, 1};
   if (!configured) {
-    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Tile::SMEM_DOUBLES * (int)sizeof(double)));
     for (int e = 0; e < 2; ++e) {
-      PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[e], pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB>, NT,
+      PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[e], pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US>, NT,
                                                                    Tile::smem_doubles(e != 0) * sizeof(double)));
       if (ctas_per_sm[e] < 1) return PMG_ERR_CUDA;
     }
@@ -161,7 +161,7 @@ static int launch_sweep(const pmgk_level *lv, int mode, const double *u, const d
   const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
   if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
   if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
-  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB><<<grid, NT, smem_bytes, stream>>>(p);
+  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US><<<grid, NT, smem_bytes, stream>>>(p);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
@@ -173,8 +173,8 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
   if (lv->tile_variant < 2) { /* default: the line-marching kernel */
     switch (lv->degree) {
-#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB) \
-  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB>(lv, mode, u, b, xold, out, f1, f2, s, geom);
+#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
+  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US>(lv, mode, u, b, xold, out, f1, f2, s, geom);
 #include "pmg_apply_sweep_tiles.inc"
 #undef PMG_SWEEP_CASE
       default: return PMG_ERR_UNSUPPORTED;

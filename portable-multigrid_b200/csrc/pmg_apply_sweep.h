@@ -19,10 +19,10 @@
 //    of the vertex DoF shared with the next cell in a register: complete results, no cross-thread sums, no
 //    atomics, and the halo a CTA recomputes for its neighbours shrinks to one partial cell per line.
 //  * CTA = BX x BY cell columns, marching through cell layers in z, LZ layers (LZ P dof planes) per step:
-//      stage    every input stream reaches shared memory through the bulk async copy engine (cp.async.bulk, SASS
-//               UBLKCP, completion on an mbarrier): one instruction per tile row, issued a full step ahead for u (two
-//               staging buffers) and two phases ahead for the epilogue's b and x_old rows; no thread spends registers on
-//               loads.  The engine wants 16-byte aligned rows while dof rows start at any 8-byte address (odd row
+//      stage    u reaches shared memory through the bulk async copy engine (cp.async.bulk, SASS UBLKCP, completion on an
+//               mbarrier): one instruction per tile row, issued a full step ahead into one of two staging buffers; the
+//               epilogue's b and x_old rows arrive by cp.async (LDGSTS) issued by the warp that phase 1 leaves idle; no
+//               thread spends registers on loads.  The engine wants 16-byte aligned rows while dof rows start at any 8-byte address (odd row
 //               lengths): a row is fetched from the aligned address below it and read back through a one-element shift
 //               that depends on the row.  (2-D TMA tensor tiles -- one instruction per plane -- would be the better fit,
 //               but UTMALDG raises "illegal instruction" on this pool's B200s even for the CUDA programming guide's
@@ -103,6 +103,22 @@ PMG_HD void pmg_mbar_wait(uint64_t *bar, int parity)
   (void)bar; (void)parity;
 #endif
 }
+// 8-byte asynchronous global -> shared copy (LDGSTS) and the wait for all of the thread's copies
+PMG_HD void pmg_sweep_cp_async8(double *dst_smem, const double *src_global)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_global) : "memory");
+#else
+  *dst_smem = *src_global;
+#endif
+}
+PMG_HD void pmg_sweep_cp_async_wait_all()
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
 // copy `bytes` (multiple of 16) from 16-byte aligned global memory to 16-byte aligned shared memory
 PMG_HD void pmg_bulk_copy(double *dst_smem, const double *src_global, int bytes, uint64_t *bar)
 {
@@ -178,8 +194,10 @@ PMG_HD constexpr int pmg_sweep_canon(int i, int j)
   return m;
 }
 
-// P: degree; BX x BY: cell columns per CTA; LZ: cell layers per step; NT_: threads
-template <int P, int BX, int BY, int LZ, int NT_>
+// P: degree; BX x BY: cell columns per CTA; LZ: cell layers per step; NT_: threads; US: 1 = in APPLY mode every second
+// row of the u tile is fetched by the loader warp's cp.async instead of the copy engine (measured: +5 % at Q4, +2 % at Q2,
+// -4 % at Q3; in the fused modes the loader warp is busy with the b / x_old rows and the split costs 15 %)
+template <int P, int BX, int BY, int LZ, int NT_, int US = 0>
 struct PmgSweepTile {
   static constexpr int N1 = P + 1;
   static constexpr int NT = NT_;
@@ -191,7 +209,7 @@ struct PmgSweepTile {
   // staging buffers (bulk-copy targets): a row is fetched from the 16-byte aligned address at or below its first
   // element, so it holds one extra element and its pitch is even; element x of row (k, y) is at [x + shift(k, y)]
   static constexpr int XPA = (XW | 1) + 1;    // elements per copied u row = pitch of A
-  static constexpr int XPE = (CW | 1) + 1;    // elements per copied b / x_old row = pitch of E
+  static constexpr int XPE = CW | 1;          // pitch of E: b / x_old rows of the owned columns (filled with cp.async)
   static constexpr int APLANE = YW * XPA, EPLANE = RW * XPE;
   static constexpr int ABUF = NPS * APLANE;   // one u staging buffer
   static constexpr int EBUF = NPS * EPLANE;   // one epilogue array (b or x_old)
@@ -202,7 +220,10 @@ struct PmgSweepTile {
   static constexpr int C_OFFSET = 2 * ABUF, D_OFFSET = C_OFFSET + CBUF;
   static constexpr int E_OFFSET = D_OFFSET + CBUF; // b boxes, then x_old boxes (not allocated for APPLY)
   static constexpr int BAR_OFFSET_APPLY = E_OFFSET, BAR_OFFSET_EPI = E_OFFSET + 2 * EBUF;
-  static constexpr int NBAR = 3;              // mbarriers: u buffer 0, u buffer 1, E
+  static constexpr int NBAR = 2;              // mbarriers: u buffer 0, u buffer 1
+  // E loader: the CTA's last warp (idle in phase 1: NITEM1 <= NT - 32 for the shipped tiles), LD_LPR lanes per row
+  static constexpr int LD_LPR = (CW - 1 <= 16) ? 16 : 32;
+  static constexpr int LD_RPI = 32 / LD_LPR;  // rows per warp instruction
   static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return (epilogue_inputs ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
   static constexpr int SMEM_DOUBLES = BAR_OFFSET_EPI + NBAR;
   static constexpr int NITEM1 = XW * NPS;
@@ -230,7 +251,7 @@ struct PmgSweepTile {
     int x_end, y_end; // tile touches the high end of the mesh (owns the last vertex line)
     int cw, rows;     // owned dof columns / rows
     int nxodd, plodd; // parities of Nx and of Nx * Ny: how the row shift changes from row to row / plane to plane
-    int64_t eA, eE;   // element index (local vector) of tile point (xl=0, yl=0) resp. (ox=0, oy=0) in local plane 0
+    int64_t eA;       // element index (local vector) of tile point (xl=0, yl=0) in local plane 0
     int64_t n_local;  // elements of the local vector
     bool has_e, has_xo; // the mode reads b / x_old
   };
@@ -247,7 +268,6 @@ struct PmgSweepTile {
     t.rows = t.ncy * P + t.y_end;
     t.nxodd = p.Nx & 1; t.plodd = (p.Nx & 1) & (p.Ny & 1);
     t.eA = (int64_t)((t.cy0 - 1) * P) * p.Nx + (t.cx0 - 1) * P;
-    t.eE = (int64_t)(t.cy0 * P) * p.Nx + t.cx0 * P;
     t.n_local = (int64_t)p.Nx * p.Ny * p.nzl;
     t.has_e = (p.mode != PMG_MODE_APPLY);
     t.has_xo = (p.mode == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
@@ -306,6 +326,33 @@ struct PmgSweepTile {
     return nelem * 8;
   }
 
+  // which rows of the u tile the loader warp fetches with cp.async instead of the copy engine
+  static PMG_HD bool row_by_loader(const TileGeom &t, int yl) { return US == 1 && !t.has_e && (yl & 1); }
+
+  // the loader warp's share of the u planes gz0 .. gz0+npl-1: lane = x point, same row layout (shift) as the bulk copies
+  static PMG_HD void load_u_async(const PmgSweepParams<P> &p, const TileGeom &t, int lane, double *A, int gz0, int npl)
+  {
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    const int yl_lo = (t.cy0 == 0) ? P : 0, yl_hi = (t.ncy + 1) * P;
+    const int y0 = yl_lo | 1; // first odd row
+    if (!row_by_loader(t, y0)) return;
+#pragma unroll
+    for (int xl = lane; xl < XW; xl += 32) {
+      const int gx = (t.cx0 - 1) * P + xl;
+      if (gx < 0 || gx >= p.Nx) continue;
+#pragma unroll
+      for (int k = 0; k < NPS; ++k) {
+        if (k >= npl) break;
+        int64_t e = t.eA + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)y0 * p.Nx; // element index of the row's xl = 0
+        double *dst = A + k * APLANE + y0 * XPA + xl;
+        for (int yl = y0; yl <= yl_hi; yl += 2) {
+          pmg_sweep_cp_async8(dst + shift_of(e), p.u + e + xl);
+          e += 2 * (int64_t)p.Nx; dst += 2 * XPA;
+        }
+      }
+    }
+  }
+
   // u planes gz0 .. gz0+npl-1 (tile footprint XW x YW) -> A
   static PMG_HD void stage_u(const PmgSweepParams<P> &p, const TileGeom &t, int tid, double *A, uint64_t *bar, int gz0, int npl)
   {
@@ -315,24 +362,47 @@ struct PmgSweepTile {
     int bytes = 0;
     for (int i = tid; i < npl * nrow; i += NT) {
       const int k = i / nrow, yl = yl_lo + (i - k * nrow);
+      if (row_by_loader(t, yl)) continue;
       bytes += issue_row(p.u, t.eA + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)yl * p.Nx, XPA, t.n_local,
                          A + k * APLANE + yl * XPA, bar);
     }
     pmg_mbar_arrive_expect(bar, bytes);
   }
 
-  // b (and x_old) rows of the owned columns of output planes gz0 .. gz0+npl-1 -> E
-  static PMG_HD void stage_e(const PmgSweepParams<P> &p, const TileGeom &t, int tid, double *E, uint64_t *bar, int gz0, int npl)
+  // b (and x_old) rows of the owned columns of output planes gz0 .. gz0+npl-1 -> E with cp.async (LDGSTS), issued by the
+  // CTA's last warp while the others do the y sweep; the warp waits for them at the end of phase 2.  (These rows as bulk
+  // copies as well saturate the copy engine -- ~1 small row per 25-35 cycles per SM, measured -- and cp.async stalls its
+  // issuer on the address registers, which an otherwise idle warp can afford.)
+  static PMG_HD void load_e_async(const PmgSweepParams<P> &p, const TileGeom &t, int lane, double *E, int gz0, int npl)
   {
     const int64_t plane = (int64_t)p.Nx * p.Ny;
-    int bytes = 0;
-    for (int i = tid; i < npl * t.rows; i += NT) {
-      const int k = i / t.rows, r = i - k * t.rows;
-      const int64_t e = t.eE + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)r * p.Nx;
-      bytes += issue_row(p.b, e, XPE, t.n_local, E + k * EPLANE + r * XPE, bar);
-      if (t.has_xo) bytes += issue_row(p.xold, e, XPE, t.n_local, E + EBUF + k * EPLANE + r * XPE, bar);
+    const int x = lane % LD_LPR, rsub = lane / LD_LPR;
+    const int64_t g0 = (int64_t)(gz0 - p.z0) * plane + (int64_t)(t.cy0 * P + rsub) * p.Nx + t.cx0 * P + x;
+    const int64_t rstep = (int64_t)LD_RPI * p.Nx;
+    const bool xok = (x < t.cw);
+#pragma unroll
+    for (int arr = 0; arr < 2; ++arr) {
+      if (arr == 1 && !t.has_xo) break;
+      const double *base = (arr == 0 ? p.b : p.xold);
+#pragma unroll
+      for (int k = 0; k < NPS; ++k) {
+        if (k >= npl) break;
+        const double *src = base + g0 + k * plane;
+        double *dst = E + arr * EBUF + k * EPLANE + rsub * XPE + x;
+#pragma unroll 4
+        for (int r = rsub; r < t.rows; r += LD_RPI) {
+          if (xok) pmg_sweep_cp_async8(dst, src);
+          src += rstep; dst += LD_RPI * XPE;
+        }
+      }
+      // columns beyond the LD_LPR lanes (the mesh's last vertex line): one element per (plane, row)
+      for (int xx = LD_LPR; xx < t.cw; ++xx)
+        for (int i = lane; i < npl * t.rows; i += 32) {
+          const int k = i / t.rows, r = i - k * t.rows;
+          pmg_sweep_cp_async8(E + arr * EBUF + k * EPLANE + r * XPE + xx,
+                        base + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)(t.cy0 * P + r) * p.Nx + t.cx0 * P + xx);
+        }
     }
-    pmg_mbar_arrive_expect(bar, bytes);
   }
 
   // ---- phase 1: y sweep.  item = (xl, k): column xl of plane k of A (u, read only) -> c in C, d in D -------------
@@ -492,7 +562,7 @@ struct PmgSweepTile {
 #pragma unroll
       for (int kp = 0; kp < N1; ++kp) top = fma(PMG_MZ(P, kp), g[kp], fma(PMG_KZ(P, kp), m[kp], top));
       // shifts of this column's rows in dof plane cz0 P; plane cz0 P + q has them flipped for odd q when Nx Ny is odd
-      const int sa = shift_of(t.eA + zoff + (int64_t)(oy + P) * p.Nx), se = shift_of(t.eE + zoff + (int64_t)oy * p.Nx);
+      const int sa = shift_of(t.eA + zoff + (int64_t)(oy + P) * p.Nx);
       const double *Uc = A + (oy + P) * XPA + P + ox;
       const double *Ec = E + oy * XPE + ox;
       const int qt = l * P + P;          // the layer's top plane
@@ -513,8 +583,8 @@ struct PmgSweepTile {
             const int fl = (q & 1) & t.plodd;
             double uc = 0.0, bb = 0.0, xo = 0.0, dinv = 1.0;
             if (MODE != PMG_MODE_APPLY || dir) uc = (q == 0) ? st.uP[ci] : Uc[(q - 1) * APLANE + (sa ^ fl)];
-            if (MODE != PMG_MODE_APPLY) bb = Ec[q * EPLANE + (se ^ fl)];
-            if (has_xo) xo = Ec[EBUF + q * EPLANE + (se ^ fl)];
+            if (MODE != PMG_MODE_APPLY) bb = Ec[q * EPLANE];
+            if (has_xo) xo = Ec[EBUF + q * EPLANE];
             if (MODE >= PMG_MODE_CHEB_FIRST) {
               if (p.dinv_vec) dinv = p.dinv_vec[glayer + (int64_t)oy * p.Nx + ox + k * plane];
               else if (FULL) dinv = st.dinv[ci][k];
@@ -623,9 +693,9 @@ struct PmgSweepTile {
     const int cz_first = halo ? cz_begin - 1 : cz_begin;
     double *Cb = smem + C_OFFSET, *Db = smem + D_OFFSET, *E = smem + E_OFFSET;
     uint64_t *bars = (uint64_t *)(smem + (t.has_e ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY));
-    int par_u[2] = {0, 0}, par_e = 0; // phase parity each barrier completes next
+    int par_u[2] = {0, 0}; // phase parity each barrier completes next
 
-    // prologue: plane 0 of the first layer -> buffer 0; the first step's planes -> buffer 1, its b / x_old rows -> E
+    // prologue: plane 0 of the first layer -> buffer 0; the first step's planes -> buffer 1
     int n0 = cz_end - cz_first; if (n0 > LZ) n0 = LZ;
     ex.for_each_thread([&](int tid, ThreadState &) {
       if (tid == 0) {
@@ -637,8 +707,13 @@ struct PmgSweepTile {
     ex.for_each_thread([&](int tid, ThreadState &) {
       stage_u(p, t, tid, smem, bars + 0, cz_first * P, 1);
       stage_u(p, t, tid, smem + ABUF, bars + 1, cz_first * P + 1, n0 * P);
-      if (t.has_e) stage_e(p, t, tid, E, bars + 2, cz_first * P, n0 * P);
+      if (tid >= NT - 32) {
+        load_u_async(p, t, tid - (NT - 32), smem, cz_first * P, 1);
+        load_u_async(p, t, tid - (NT - 32), smem + ABUF, cz_first * P + 1, n0 * P);
+        pmg_sweep_cp_async_wait_all();
+      }
     });
+    ex.sync();
     ex.for_each_thread([&](int tid, ThreadState &st) {
       decode(p, t, tid, st);
       pmg_mbar_wait(bars + 0, par_u[0]);
@@ -658,21 +733,23 @@ struct PmgSweepTile {
       int nnext = cz_end - (cz + LZ); if (nnext > LZ) nnext = LZ;
       ex.for_each_thread([&](int tid, ThreadState &) {
         // the other staging buffer and E were last read before the barrier that ended the previous step: fetch the next
-        // step's u planes (a full step ahead) and this step's b / x_old rows (two phases ahead)
+        // step's u planes (a full step ahead) and, by the last warp, this step's b / x_old rows (two phases ahead)
         if (nnext > 0) stage_u(p, t, tid, smem + (cur ^ 1) * ABUF, bars + (cur ^ 1), (cz + LZ) * P + 1, nnext * P);
-        if (t.has_e && cz > cz_first) stage_e(p, t, tid, E, bars + 2, cz * P, nlay * P);
+        if (tid >= NT - 32) {
+          if (t.has_e) load_e_async(p, t, tid - (NT - 32), E, cz * P, nlay * P);
+          if (nnext > 0) load_u_async(p, t, tid - (NT - 32), smem + (cur ^ 1) * ABUF, (cz + LZ) * P + 1, nnext * P);
+        }
         pmg_mbar_wait(bars + cur, par_u[cur]);
         phase1(p, t, tid, A, Cb, Db, cz * P + 1, nlay * P);
       });
       par_u[cur] ^= 1;
       ex.sync();
-      ex.for_each_thread([&](int, ThreadState &st) { phase2(p, t, st, Cb, Db, nlay * P); });
-      ex.sync();
-      ex.for_each_thread([&](int, ThreadState &st) {
-        if (t.has_e) pmg_mbar_wait(bars + 2, par_e);
-        phase3(p, t, st, A, Cb, Db, E, cz, nlay, cz_begin);
+      ex.for_each_thread([&](int tid, ThreadState &st) {
+        phase2(p, t, st, Cb, Db, nlay * P);
+        if (tid >= NT - 32) pmg_sweep_cp_async_wait_all(); // the loader warp's copies (E for phase 3, u rows for the next step)
       });
-      par_e ^= 1;
+      ex.sync();
+      ex.for_each_thread([&](int, ThreadState &st) { phase3(p, t, st, A, Cb, Db, E, cz, nlay, cz_begin); });
       ex.sync();
       cur ^= 1;
     }

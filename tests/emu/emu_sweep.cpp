@@ -14,13 +14,13 @@ struct SweepHostExec {
   void sync() {}
 };
 
-template <int P, int BX, int BY, int LZ, int NT>
+template <int P, int BX, int BY, int LZ, int NT, int US = 1>
 static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
                      int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -85,7 +85,7 @@ extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, un
     return -3;
   }
   switch (degree) {
-#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB) case P: sweep_go<P, BX, BY, LZ, NT>(ARGS); return 0;
+#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) case P: sweep_go<P, BX, BY, LZ, NT, US>(ARGS); return 0;
 #include "pmg_apply_sweep_tiles.inc"
 #undef PMG_SWEEP_CASE
   }

@@ -9,7 +9,10 @@
 #include "pmg_apply_sweep.h"
 extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #define PP C_P
-#define CFG C_P, C_BX, C_BY, C_LZ, C_NT
+#ifndef C_US
+#define C_US 0
+#endif
+#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US
 #define STR2(x) #x
 #define STR(x) STR2(x)
 #define CFGSTR STR(C_P) "," STR(C_BX) "," STR(C_BY) "," STR(C_LZ) "," STR(C_NT)
