@@ -229,6 +229,10 @@ struct PmgSweepTile {
   static constexpr int NITEM1 = XW * NPS;
   static constexpr int IT2 = (RW * NPS + NT - 1) / NT; // phase-2 items per thread
   static constexpr int NCOL = (CW * RW + NT - 1) / NT; // dof columns per thread in phase 3
+  static_assert(NT % 32 == 0, "whole warps: the last one is the cp.async loader");
+  static_assert(CW <= 255 && RW <= 255, "column coordinates are packed into 8 bits each (ThreadState::info)");
+  static_assert(P + 2 <= 15, "position types are packed into 4 bits each");
+  static_assert(SMEM_DOUBLES * 8 <= 227 * 1024, "tile does not fit the 227 KB of shared memory of a CTA");
 
 #define PMG_M(i, j) p.M[pmg_sweep_canon<P>(i, j)]
 #define PMG_KX(i, j) p.Kx[pmg_sweep_canon<P>(i, j)]
