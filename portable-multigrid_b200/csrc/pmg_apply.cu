@@ -171,7 +171,14 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
                     double *out, double f1, double f2, cudaStream_t s, int *geom)
 {
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
-  if (lv->tile_variant < 2) { /* default: the line-marching kernel */
+  /* tile_variant 0 (default): the line-marching kernel for levels large enough to fill its copy pipeline, the cell-tile
+     kernel (direct loads, no staging prologue) for the small coarse levels, where launch-to-result latency is everything:
+     measured on B200 (tools/small_levels.py) 5.6-7.2 us against 7.0-12.3 us per fused step for Q1 up to 32^3 cells and
+     12.3 against 16.4 us for Q2 on 32^3; from 64^3 cells on the line-marching kernel wins (14.3 : 17.1, 38.9 : 55.3 us).
+     1 = line-marching always; 2, 3 = cell-tile always (small / large tiles). */
+  const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
+  const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
+  if (lv->tile_variant == 1 || (lv->tile_variant == 0 && !small_level)) {
     switch (lv->degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
   case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US>(lv, mode, u, b, xold, out, f1, f2, s, geom);

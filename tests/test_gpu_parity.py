@@ -14,6 +14,18 @@ APPLY_TOL = 1e-12
 HISTORY_TOL = 1e-10
 
 
+@pytest.fixture(autouse=True, params=["auto", "sweep", "celltile"])
+def apply_kernel(request, monkeypatch):
+    """Every test runs with the library's default choice of apply kernel (line-marching kernel for large levels, cell-tile
+    kernel for small ones) and with each of the two forced: the meshes here are small, so the default alone would never
+    reach the line-marching kernel.  PMG_TILE_VARIANT is read when an operator is created."""
+    if request.param == "auto":
+        monkeypatch.delenv("PMG_TILE_VARIANT", raising=False)
+    else:
+        monkeypatch.setenv("PMG_TILE_VARIANT", "1" if request.param == "sweep" else "2")
+    return request.param
+
+
 def _oracle_levels(oracle, levels, faces=0x3F):
     return [oracle.MatrixFree(3, p, n, faces=faces) for (p, n) in levels]
 
