@@ -365,18 +365,23 @@ struct DiagGeom {
 
 __device__ __forceinline__ int pos_type(int g, int N, int P) { return (g == 0) ? P : (g == N - 1) ? P + 1 : g % P; }
 
+// one CTA row per (plane, y-row) pair: no integer division per element
 __global__ void k_dinv(const DiagGeom g, const double *__restrict__ tab, double f, const double *b, double *out)
 {
-  const int64_t plane = (int64_t)g.Nx * g.Ny;
-  const int64_t total = plane * (g.z_hi - g.z_lo);
   const int T = g.P + 2;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int gx = (int)(idx % g.Nx), gy = (int)((idx / g.Nx) % g.Ny), gz = g.z_lo + (int)(idx / plane);
-    const int64_t l = (int64_t)(gz - g.z0) * plane + (int64_t)gy * g.Nx + gx;
-    double d;
-    if (on_dirichlet(gx, gy, gz, g.Nx, g.Ny, g.Nz, g.faces)) d = 1.0;
-    else d = tab[pos_type(gx, g.Nx, g.P) + T * (pos_type(gy, g.Ny, g.P) + T * pos_type(gz, g.Nz, g.P))];
-    out[l] = b ? f * d * b[l] : d;
+  const int nrows = g.Ny * (g.z_hi - g.z_lo);
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int gy = row % g.Ny, gz = g.z_lo + row / g.Ny;
+    const bool dyz = (gy == 0 && (g.faces >> 2 & 1u)) || (gy == g.Ny - 1 && (g.faces >> 3 & 1u)) ||
+                     (gz == 0 && (g.faces >> 4 & 1u)) || (gz == g.Nz - 1 && (g.faces >> 5 & 1u));
+    const int tyz = T * (pos_type(gy, g.Ny, g.P) + T * pos_type(gz, g.Nz, g.P));
+    const int64_t l0 = ((int64_t)(gz - g.z0) * g.Ny + gy) * g.Nx;
+    for (int gx = threadIdx.x; gx < g.Nx; gx += blockDim.x) {
+      const bool dir = dyz || (gx == 0 && (g.faces & 1u)) || (gx == g.Nx - 1 && (g.faces >> 1 & 1u));
+      const int tx = (gx == 0) ? g.P : (gx == g.Nx - 1) ? g.P + 1 : gx % g.P;
+      const double d = dir ? 1.0 : tab[tx + tyz];
+      out[l0 + gx] = b ? f * d * b[l0 + gx] : d;
+    }
   }
 }
 
@@ -398,7 +403,11 @@ int launch_dinv(const pmgk_level *lv, double f, const double *b, double *out, cu
   if (nb > cap) nb = cap;
   if (nb < 1) return 0;
   if (b && lv->dinv_vec) k_dinv_vec<<<(unsigned)nb, 256, 0, s>>>(lv->dinv_vec, f, b, out, total);
-  else k_dinv<<<(unsigned)nb, 256, 0, s>>>(g, lv->dinv_tab, f, b, out);
+  else {
+    int64_t rows = (int64_t)lv->Ny * lv->nzl;
+    if (rows > (int64_t)cap * 4) rows = (int64_t)cap * 4;
+    k_dinv<<<(unsigned)rows, lv->Nx >= 192 ? 256 : (lv->Nx >= 96 ? 128 : (lv->Nx >= 48 ? 64 : 32)), 0, s>>>(g, lv->dinv_tab, f, b, out);
+  }
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
