@@ -54,12 +54,29 @@ def hp_levels(p, cells):
     return levels[::-1]
 
 
-def workload_name(p, cells, world):
+def h_levels(p, cells):
+    """(degree, (nx,ny,nz)) coarse -> fine: the same degree on every level of the refinement hierarchy
+    (reference geometric_multigrid driver)."""
+    levels = [(p, tuple(cells))]
+    c = list(cells)
+    while all(x % 2 == 0 for x in c) and min(c) > 1:
+        c = [x // 2 for x in c]
+        levels.append((p, tuple(c)))
+    return levels[::-1]
+
+
+# BASELINE.json configs: "c2" = configs[1] (the one the metric is quoted on, default), "c1" = configs[0]
+CONFIGS = {"c2": {"degree": 4, "cells": 64, "hierarchy": "hp", "cheb_degree": 5},
+           "c1": {"degree": 2, "cells": 64, "hierarchy": "h", "cheb_degree": 3}}
+
+
+def workload_name(p, cells, world, hierarchy="hp", cheb_degree=5):
     nd = 1
     for c in cells:
         nd *= c * p + 1
-    return ("3D Poisson Q%d, %dx%dx%d cells (%d DoFs), hp-multigrid p=4->2->1 + geometric levels, V(2,2) "
-            "Chebyshev(5)-Jacobi, one V-cycle per step" % (p, cells[0], cells[1], cells[2], nd)), nd
+    hier = "hp-multigrid p=4->2->1 + geometric levels" if hierarchy == "hp" else "geometric multigrid, Q%d on every level" % p
+    return ("3D Poisson Q%d, %dx%dx%d cells (%d DoFs), %s, V(2,2) Chebyshev(%d)-Jacobi, one V-cycle per step"
+            % (p, cells[0], cells[1], cells[2], nd, hier, cheb_degree)), nd
 
 
 class ClockSampler:
@@ -184,9 +201,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--degree", type=int, default=DEGREE)
-    ap.add_argument("--cells", type=int, default=CELLS)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json workload (default: the one the metric is quoted on)")
+    ap.add_argument("--degree", type=int, default=None)
+    ap.add_argument("--cells", type=int, default=None)
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.degree is not None:
+        cfg["degree"] = args.degree
+    if args.cells is not None:
+        cfg["cells"] = args.cells
     if args.impl == "reference":
         return run_reference(args)
 
@@ -225,11 +248,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    p = args.degree
-    cells = scaled_cells(args.cells, world)
-    levels = hp_levels(p, cells)
-    name, n_dofs = workload_name(p, cells, world)
-    ops, transfers, smoothers, mg = G.build_hierarchy(ctx, levels)
+    p = cfg["degree"]
+    cells = scaled_cells(cfg["cells"], world)
+    levels = hp_levels(p, cells) if cfg["hierarchy"] == "hp" else h_levels(p, cells)
+    name, n_dofs = workload_name(p, cells, world, cfg["hierarchy"], cfg["cheb_degree"])
+    ops, transfers, smoothers, mg = G.build_hierarchy(ctx, levels, degree=cfg["cheb_degree"])
     top = ops[-1]
     r_host = splitmix_src(n_dofs)
     r, z = top.vector_from(r_host), top.initialize_dof_vector()
@@ -270,6 +293,19 @@ def main():
     for _ in range(3):
         top.chebyshev_step(xo, u, xo, b, 0.3, 0.1)
     ms_step = timed(lambda: top.chebyshev_step(xo, u, xo, b, 0.3, 0.1), 20)
+
+    # the drivers' solve (program.cc:345-355): CG preconditioned by one V-cycle, to 1e-12 ||b||, on the load vector of f = 1
+    rhs, sol = top.initialize_dof_vector(), top.initialize_dof_vector()
+    top.assemble_rhs(rhs)
+    G.cg_solve(top, sol, rhs, mg)  # warm-up (also leaves the graph captured)
+    sol.set(0.0)
+    barrier()
+    t0 = time.perf_counter()
+    cg_it, cg_hist, cg_rc = G.cg_solve(top, sol, rhs, mg)
+    ctx.sync()
+    cg_s = max_over_ranks(time.perf_counter() - t0)
+    cg = {"iterations": int(cg_it), "converged": cg_rc == 0, "ms": cg_s * 1e3, "gdofs_x_iterations_per_s": n_dofs * max(cg_it, 1) / cg_s / 1e9,
+          "final_relative_residual": float(cg_hist[-1] / cg_hist[0]) if len(cg_hist) and cg_hist[0] > 0 else None}
 
     # end to end through the host-buffer entry point: pinned host memory, H2D + V-cycle + D2H every step
     n_local_bytes = n_dofs * 8
@@ -333,6 +369,7 @@ def main():
                    "parallelism": "z-slabs x%d" % world, "cuda_graph": True},
         "apply_gdofs": n_dofs / (ms_apply * 1e-3) / 1e9, "apply_ms": ms_apply,
         "apply_hbm_frac": 16.0 * n_local / (ms_apply * 1e-3) / 1e9 / peak,
+        "cg_solve": cg,
         "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
         "clocks": clocks,
         "roofline": {"kernel": "pmg_sweep_kernel<%d> (fused Chebyshev step, finest level)" % p, "bound": "hbm", "achieved": achieved, "peak": peak,

@@ -92,6 +92,7 @@ struct pmg_operator {
   pmgk_level lv;
   double *d_dinv_tab;
   pmg_vector *dinv;      /* explicit inverse diagonal once compute_diagonal() ran */
+  pmg_vector *cg_ws[4];  /* CG work vectors r, z, p, Ap: created by the first pmg_cg_solve, kept until destroy */
 };
 
 struct pmg_transfer {

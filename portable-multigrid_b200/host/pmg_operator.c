@@ -57,6 +57,7 @@ int pmg_laplace_operator_destroy(pmg_operator *op)
   if (!op) return PMG_OK;
   cudaStreamSynchronize(op->ctx->stream);
   if (op->dinv) pmg_vector_destroy(op->dinv);
+  for (int i = 0; i < 4; ++i) if (op->cg_ws[i]) pmg_vector_destroy(op->cg_ws[i]);
   cudaFree(op->d_dinv_tab);
   free(op);
   return PMG_OK;

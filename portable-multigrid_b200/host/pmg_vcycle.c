@@ -242,11 +242,12 @@ int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_
   }
   pmg_context *ctx = A->ctx;
   const pmg_layout *l = &A->lay;
-  pmg_vector *r = NULL, *z = NULL, *p = NULL, *Ap = NULL;
-  PMG_CHECK(pmg_vector_create_layout(ctx, l, &r));
-  PMG_CHECK(pmg_vector_create_layout(ctx, l, &z));
-  PMG_CHECK(pmg_vector_create_layout(ctx, l, &p));
-  PMG_CHECK(pmg_vector_create_layout(ctx, l, &Ap));
+  /* work vectors live with the operator (the reference's SolverCG keeps them in a GrowingVectorMemory pool): a
+     cudaMalloc / cudaFree pair of four fine-level vectors per solve costs more than the iterations at C2 */
+  pmg_operator *Aw = (pmg_operator *)A;
+  for (int i = 0; i < 4; ++i)
+    if (!Aw->cg_ws[i]) PMG_CHECK(pmg_vector_create_layout(ctx, l, &Aw->cg_ws[i]));
+  pmg_vector *r = Aw->cg_ws[0], *z = Aw->cg_ws[1], *p = Aw->cg_ws[2], *Ap = Aw->cg_ws[3];
   int it = 0, converged = 0, rc = PMG_OK;
   double res = 0.0, rz = 0.0;
 #define CG(call) do { rc = (call); if (rc != PMG_OK) goto done; } while (0)
@@ -292,7 +293,6 @@ int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_
 #undef CG
 done:
   if (last_step) *last_step = it;
-  pmg_vector_destroy(r); pmg_vector_destroy(z); pmg_vector_destroy(p); pmg_vector_destroy(Ap);
   if (rc != PMG_OK) return rc;
   if (!converged) { pmg_set_error("CG did not converge in %d iterations (residual %g, tolerance %g)", it, res, tol); return PMG_ERR_NOT_CONVERGED; }
   return PMG_OK;
