@@ -197,6 +197,138 @@ __global__ void __launch_bounds__(256) k_restrict_cells(const XferGeom g, const 
   }
 }
 
+// ---- column kernels for compile-time sizes ---------------------------------------------------------------
+// Thread = one (xf, yf) column of a coarse cell's fine patch; CPB cells, consecutive in x, per CTA; grid = (x groups, cy,
+// local cz): no integer division on the data path and ~20 instructions per fine dof (the generic kernels above: ~400,
+// issue bound).  Lane order xf fastest, then cell: a warp touches consecutive fine dofs of one row.
+
+// fine dof (xf, yf, zf) of cell (cx, cy, cz) belongs to this patch (low-side ownership) and is not constrained
+__device__ __forceinline__ bool xfer_col_owned(const XferGeom &g, int NF, int cx, int cy, int xf, int yf, int gx, int gy)
+{
+  if ((xf == NF - 1 && cx != g.ncx - 1) || (yf == NF - 1 && cy != g.ncy - 1)) return false;
+  return !((gx == 0 && (g.faces & 1u)) || (gx == g.Nfx - 1 && (g.faces >> 1 & 1u)) || (gy == 0 && (g.faces >> 2 & 1u)) ||
+           (gy == g.Nfy - 1 && (g.faces >> 3 & 1u)));
+}
+
+template <int CPB, int NC, int NF>
+__global__ void __launch_bounds__(CPB *NF *NF) k_prolongate_col(const XferGeom g, const double *__restrict__ P1d, double *dst,
+                                                               const double *__restrict__ src)
+{
+  __shared__ double sP[NC * NF];
+  __shared__ double vc[CPB][NC * NC * NC];
+  const int tid = threadIdx.x;
+  const int xf = tid % NF, c = (tid / NF) % CPB, yf = tid / (NF * CPB);
+  const int cx0 = blockIdx.x * CPB, cy = blockIdx.y, cz = g.ccz_lo + blockIdx.z;
+  for (int i = tid; i < NC * NF; i += CPB * NF * NF) sP[i] = P1d[i];
+  // coarse values of the CTA's cells (h: constrained coarse dofs read as 0, :170-173; p: read unmasked, :115-121)
+  for (int w = tid; w < CPB * NC * NC * NC; w += CPB * NF * NF) {
+    const int cc = w / (NC * NC * NC), i = w % (NC * NC * NC);
+    const int ix = i % NC, iy = (i / NC) % NC, iz = i / (NC * NC);
+    const int cx = cx0 + cc;
+    double v = 0.0;
+    if (cx < g.ncx) {
+      const int gx = cx * g.pc + ix, gy = cy * g.pc + iy, gz = cz * g.pc + iz;
+      if (g.kind == 1 || !on_dirichlet(gx, gy, gz, g.Ncx, g.Ncy, g.Ncz, g.faces))
+        v = src[((int64_t)(gz - g.c_z0) * g.Ncy + gy) * g.Ncx + gx];
+    }
+    vc[cc][i] = v;
+  }
+  __syncthreads();
+  const int cx = cx0 + c;
+  if (cx >= g.ncx) return;
+  const int gx = cx * g.fstep + xf, gy = cy * g.fstep + yf;
+  if (!xfer_col_owned(g, NF, cx, cy, xf, yf, gx, gy)) return;
+  // x and y contractions for this column: t[iz] = sum_iy P[iy][yf] sum_ix P[ix][xf] c[iz][iy][ix]
+  double t[NC];
+#pragma unroll
+  for (int iz = 0; iz < NC; ++iz) {
+    double s = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < NC; ++iy) {
+      double r = 0.0;
+#pragma unroll
+      for (int ix = 0; ix < NC; ++ix) r = fma(sP[ix * NF + xf], vc[c][(iz * NC + iy) * NC + ix], r);
+      s = fma(sP[iy * NF + yf], r, s);
+    }
+    t[iz] = s;
+  }
+  // z contraction + owner update: dst += value on owned, unconstrained fine dofs (weight 0 / masked otherwise, :1346-1349)
+  double *col = dst + ((int64_t)(cz * g.fstep - g.f_z0) * g.Nfy + gy) * g.Nfx + gx;
+  const int64_t plane = (int64_t)g.Nfx * g.Nfy;
+#pragma unroll
+  for (int zf = 0; zf < NF; ++zf) {
+    const int gz = cz * g.fstep + zf;
+    if (zf == NF - 1 && cz != g.ncz - 1) continue;
+    if (gz < g.f_zown_lo || gz >= g.f_zown_hi) continue;
+    if ((gz == 0 && (g.faces >> 4 & 1u)) || (gz == g.Nfz - 1 && (g.faces >> 5 & 1u))) continue;
+    double s = 0.0;
+#pragma unroll
+    for (int iz = 0; iz < NC; ++iz) s = fma(sP[iz * NF + zf], t[iz], s);
+    col[zf * plane] += s;
+  }
+}
+
+// pass 1 of the restriction, column form: scratch[cell][zc][yc][xc] = (P^T x P^T x P^T) applied to the patch's owned fine dofs
+template <int CPB, int NC, int NF>
+__global__ void __launch_bounds__(CPB *NF *NF) k_restrict_cells_col(const XferGeom g, const double *__restrict__ P1d, double *scratch,
+                                                                   const double *__restrict__ src)
+{
+  __shared__ double sP[NC * NF];
+  __shared__ double t1[CPB][NC][NF * NF]; // [zc][yf][xf]
+  __shared__ double t2[CPB][NC * NC][NF]; // [zc][yc][xf]
+  constexpr int NTH = CPB * NF * NF;
+  const int tid = threadIdx.x;
+  const int xf = tid % NF, c = (tid / NF) % CPB, yf = tid / (NF * CPB);
+  const int cx0 = blockIdx.x * CPB, cy = blockIdx.y, cz = g.ccz_lo + blockIdx.z;
+  for (int i = tid; i < NC * NF; i += NTH) sP[i] = P1d[i];
+  __syncthreads();
+  const int cx = cx0 + c;
+  {
+    // z contraction of this column's owned, unconstrained fine values
+    double v[NF];
+    const int gx = cx * g.fstep + xf, gy = cy * g.fstep + yf;
+    const bool live = cx < g.ncx && xfer_col_owned(g, NF, cx, cy, xf, yf, gx, gy);
+    const double *col = src + ((int64_t)(cz * g.fstep - g.f_z0) * g.Nfy + gy) * g.Nfx + gx;
+    const int64_t plane = (int64_t)g.Nfx * g.Nfy;
+#pragma unroll
+    for (int zf = 0; zf < NF; ++zf) {
+      const int gz = cz * g.fstep + zf;
+      const bool ok = live && !(zf == NF - 1 && cz != g.ncz - 1) &&
+                      !((gz == 0 && (g.faces >> 4 & 1u)) || (gz == g.Nfz - 1 && (g.faces >> 5 & 1u)));
+      v[zf] = ok ? col[zf * plane] : 0.0;
+    }
+#pragma unroll
+    for (int zc = 0; zc < NC; ++zc) {
+      double s = 0.0;
+#pragma unroll
+      for (int zf = 0; zf < NF; ++zf) s = fma(sP[zc * NF + zf], v[zf], s);
+      t1[c][zc][yf * NF + xf] = s;
+    }
+  }
+  __syncthreads();
+  // y contraction: t2[zc][yc][xf]
+  for (int w = tid; w < CPB * NC * NC * NF; w += NTH) {
+    const int x2 = w % NF, cc = (w / NF) % CPB, zy = w / (NF * CPB);
+    const int yc = zy % NC, zc = zy / NC;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) s = fma(sP[yc * NF + k], t1[cc][zc][k * NF + x2], s);
+    t2[cc][zc * NC + yc][x2] = s;
+  }
+  __syncthreads();
+  // x contraction -> scratch[cell][zc][yc][xc], cell numbered x fastest over the rank's coarse cells
+  for (int w = tid; w < CPB * NC * NC * NC; w += NTH) {
+    const int cc = w / (NC * NC * NC), r = w % (NC * NC * NC);
+    if (cx0 + cc >= g.ncx) continue;
+    const int xc = r % NC, zy = r / NC;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) s = fma(sP[xc * NF + k], t2[cc][zy][k], s);
+    const int64_t cell = ((int64_t)blockIdx.z * g.ncy + cy) * g.ncx + cx0 + cc;
+    scratch[cell * (NC * NC * NC) + r] = s;
+  }
+}
+
 // pass 2: every coarse dof of the handled layers gathers its <= 8 cell-local contributions
 __global__ void k_restrict_gather(const XferGeom g, double *dst, const double *__restrict__ scratch)
 {
@@ -298,6 +430,26 @@ static int launch_restrict(const XferGeom &g, const double *P1d, double *scratch
   return 0;
 }
 
+template <int CPB, int NC, int NF>
+static int launch_prolongate_col(const XferGeom &g, const double *P1d, double *dst, const double *src, cudaStream_t s)
+{
+  const dim3 grid((unsigned)((g.ncx + CPB - 1) / CPB), (unsigned)g.ncy, (unsigned)(g.ccz_hi - g.ccz_lo));
+  k_prolongate_col<CPB, NC, NF><<<grid, CPB * NF * NF, 0, s>>>(g, P1d, dst, src);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+template <int CPB, int NC, int NF>
+static int launch_restrict_col(const XferGeom &g, const double *P1d, double *scratch, const double *src, cudaStream_t s)
+{
+  const dim3 grid((unsigned)((g.ncx + CPB - 1) / CPB), (unsigned)g.ncy, (unsigned)(g.ccz_hi - g.ccz_lo));
+  k_restrict_cells_col<CPB, NC, NF><<<grid, CPB * NF * NF, 0, s>>>(g, P1d, scratch, src);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
 // the (NC, NF) pairs of the drivers' hierarchies get compile-time sizes: h-transfer of Q1..Q4 and the p-transfers
 // p -> p/2 (Q2->Q1 and Q4->Q2 share their sizes with the h-transfers of Q1 and Q2); everything else runs the generic code
 #define PMG_XFER_DISPATCH(LAUNCH, ...)                                                        \
@@ -316,13 +468,27 @@ static int launch_restrict(const XferGeom &g, const double *P1d, double *scratch
     }                                                                                         \
   } while (0)
 
+// column kernels (grid.y, grid.z <= 65535) for the sizes of the drivers' hierarchies; generic kernels otherwise
+#define PMG_XFER_COL(LAUNCH, ...)                                                            \
+  do {                                                                                        \
+    if (g.ncy <= 65535 && g.ccz_hi - g.ccz_lo <= 65535) {                                     \
+      if (g.NC == 2 && g.NF == 3) return LAUNCH<16, 2, 3>(__VA_ARGS__);                       \
+      if (g.NC == 3 && g.NF == 5) return LAUNCH<8, 3, 5>(__VA_ARGS__);                        \
+      if (g.NC == 2 && g.NF == 4) return LAUNCH<8, 2, 4>(__VA_ARGS__);                        \
+      if (g.NC == 4 && g.NF == 7) return LAUNCH<4, 4, 7>(__VA_ARGS__);                        \
+      if (g.NC == 5 && g.NF == 9) return LAUNCH<2, 5, 9>(__VA_ARGS__);                        \
+    }                                                                                         \
+  } while (0)
+
 static int dispatch_prolongate(const XferGeom &g, const double *P1d, double *dst, const double *src, cudaStream_t s)
 {
+  PMG_XFER_COL(launch_prolongate_col, g, P1d, dst, src, s);
   PMG_XFER_DISPATCH(launch_prolongate, g, P1d, dst, src, s);
 }
 
 static int dispatch_restrict(const XferGeom &g, const double *P1d, double *scratch, const double *src, cudaStream_t s)
 {
+  PMG_XFER_COL(launch_restrict_col, g, P1d, scratch, src, s);
   PMG_XFER_DISPATCH(launch_restrict, g, P1d, scratch, src, s);
 }
 
