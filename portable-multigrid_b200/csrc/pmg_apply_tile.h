@@ -1,4 +1,6 @@
-// pmg_apply_tile.h -- the cell-loop Laplace apply, fused with the smoother update.
+// pmg_apply_tile.h -- the cell-loop Laplace apply, fused with the smoother update: cell-tile kernel.
+// (The library launches it on the small coarse levels, where its direct loads give the lowest launch-to-result latency;
+// large levels run the line-marching kernel of pmg_apply_sweep.h.  PMG_TILE_VARIANT=2|3 forces it everywhere.)
 //
 // Replaces LaplaceOperator::vmult + LocalLaplaceOperator::operator()
 // (reference include/operators/portable_laplace_operator.h:227-381, 557-719) and the
@@ -32,29 +34,6 @@
 #else
 #define PMG_HD inline
 #endif
-
-// 8-byte asynchronous global -> shared copy (LDGSTS); a plain copy under the host emulator
-PMG_HD void pmg_cp_async8(double *dst_smem, const double *src_global)
-{
-#if defined(__CUDA_ARCH__)
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src_global) : "memory");
-#else
-  *dst_smem = *src_global;
-#endif
-}
-PMG_HD void pmg_cp_async_commit()
-{
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-#endif
-}
-PMG_HD void pmg_cp_async_wait_all()
-{
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-#endif
-}
 
 #ifndef PMG_APPLY_MODES_DEFINED
 #define PMG_APPLY_MODES_DEFINED
@@ -119,14 +98,8 @@ struct PmgApplyTile {
   // otherwise the output planes alias the exchange tile (5 barriers per layer)
   static constexpr bool ALIAS = (T1_SIZE + O_SIZE) * 8 > 200 * 1024;
   static constexpr int O_OFFSET = ALIAS ? 0 : T1_SIZE;
-  // input staging IN[k][y][x]: the P new dof planes of the NEXT cell layer, copied with cp.async while the
-  // current layer is computed; enabled when T1 + O + IN of two CTAs fit on one SM
-  static constexpr int CXD = CXC * P + 1, CYD = CYC * P + 1; // dof columns touched by the tile
-  static constexpr int IN_SIZE = P * CXD * CYD;
-  static constexpr bool STAGE_IN = false; // measured on B200 (p=2..4): 5-15 % slower than direct loads, which hit L1/L2
-  static constexpr int IN_OFFSET = T1_SIZE + O_SIZE;
-  static constexpr int SMEM_DOUBLES =
-    ALIAS ? ((T1_SIZE > O_SIZE) ? T1_SIZE : O_SIZE) : T1_SIZE + O_SIZE + (STAGE_IN ? IN_SIZE : 0);
+  static constexpr int SMEM_DOUBLES = ALIAS ? ((T1_SIZE > O_SIZE) ? T1_SIZE : O_SIZE) : T1_SIZE + O_SIZE;
+  // (staging the next layer's planes with cp.async was measured 5-15 % slower than these direct loads, which hit L1/L2)
   // epilogue iteration space: owned dof columns of the tile incl. the optional high face
   static constexpr int EW = BX * P + 1, EH = BY * P + 1;
   static constexpr int ECOLS = EW * EH;
@@ -186,21 +159,6 @@ struct PmgApplyTile {
     }
   }
 
-  // copy the P new dof planes of cell layer cz (global planes cz*P+1 .. cz*P+P, tile columns) into IN
-  static PMG_HD void stage_issue(const PmgApplyParams<P> &p, int tid, double *smem, int cx0, int cy0, int cz)
-  {
-    const int gx0 = (cx0 - 1) * P, gy0 = (cy0 - 1) * P;
-    const int64_t plane = (int64_t)p.Nx * p.Ny;
-    const double *base = p.u + (int64_t)(cz * P + 1 - p.z0) * plane;
-    double *in = smem + IN_OFFSET;
-    for (int e = tid; e < IN_SIZE; e += NT) {
-      const int x = e % CXD, y = (e / CXD) % CYD, k = e / (CXD * CYD);
-      const int gx = gx0 + x, gy = gy0 + y;
-      if (gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny) pmg_cp_async8(in + e, base + k * plane + (int64_t)gy * p.Nx + gx);
-    }
-    pmg_cp_async_commit();
-  }
-
   // ---- phases (one call per thread; separated by sync) ----------------------
   // F: load the layer's new planes, x-forward each, accumulate the z-forward sweep, publish to T1
   static PMG_HD void phase_forward(const PmgApplyParams<P> &p, ThreadState &st, double *smem, int cz, bool first_layer)
@@ -218,8 +176,6 @@ struct PmgApplyTile {
       if (k == 0 && !first_layer) {
 #pragma unroll
         for (int a = 0; a < N1; ++a) xk[a] = st.cin[a];
-      } else if (STAGE_IN && k > 0) {
-        load_xfwd(p, st, smem + IN_OFFSET + ((k - 1) * CYD + st.tcy * P + st.j) * CXD + st.tcx * P, cz * P + k, xk);
       } else {
         load_xfwd(p, st, row + k * plane, cz * P + k, xk);
       }
@@ -441,29 +397,18 @@ struct PmgApplyTile {
 
     ex.for_each_thread([&](int tid, ThreadState &st) { decode(tid, cx0, cy0, p, st); });
 
-    if (STAGE_IN) {
-      ex.for_each_thread([&](int tid, ThreadState &) { stage_issue(p, tid, smem, cx0, cy0, cz_first); pmg_cp_async_wait_all(); });
-      ex.sync();
-    }
     for (int cz = cz_first; cz < cz_end; ++cz) {
       const bool first = (cz == cz_first);
       const bool write_out = (cz >= cz_begin);
       ex.for_each_thread([&](int, ThreadState &st) { phase_forward(p, st, smem, cz, first); });
       ex.sync();
-      // every thread has consumed IN: start the copy of the next layer's planes; it lands during the y and
-      // backward phases and is waited for before the barrier that ends the backward phase
-      if (STAGE_IN && cz + 1 < cz_end)
-        ex.for_each_thread([&](int tid, ThreadState &) { stage_issue(p, tid, smem, cx0, cy0, cz + 1); });
       ex.for_each_thread([&](int tid, ThreadState &) { phase_y(p, tid, cx0, cy0, smem); });
       ex.sync();
       if (ALIAS) {
         ex.for_each_thread([&](int, ThreadState &st) { phase_back_read(st, smem); });
         ex.sync();
       }
-      ex.for_each_thread([&](int, ThreadState &st) {
-        phase_back_write(p, st, smem, first, write_out);
-        if (STAGE_IN) pmg_cp_async_wait_all();
-      });
+      ex.for_each_thread([&](int, ThreadState &st) { phase_back_write(p, st, smem, first, write_out); });
       ex.sync();
       // !ALIAS: no barrier after the epilogue: the next layer's forward and y phases only touch T1, and the
       // two barriers they end with order this read of O before the next write to it
