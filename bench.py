@@ -142,6 +142,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is meant to use all the host threads it can
+    if "LOCAL_RANK" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import pyoracle as O
