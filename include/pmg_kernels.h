@@ -66,6 +66,9 @@ int pmgk_cg_update_xr(double *x, double *r, const double *p, const double *Ap, c
 int pmgk_cg_update_p(double *p, const double *z, const double *beta_dev, int64_t n, void *stream);
 /* tiny device-scalar helper: out[0] = num[0] / den[0] */
 int pmgk_scalar_div(double *out, const double *num, const double *den, void *stream);
+/* out[(z * Ny + y) * Nx + x] = lx[x] * ly[y] * lz[z] over nz local planes (lx, ly, lz device arrays): tensor-product
+   load vector of the drivers' right-hand side (program.cc:289-334) */
+int pmgk_outer3(double *out, const double *lx, const double *ly, const double *lz, int Nx, int Ny, int nz, void *stream);
 /* x_i = ((first_global + i) mod 11), Chebyshev eigenvalue-estimate start vector */
 int pmgk_set_mod11(double *x, int64_t first_global, int64_t n, void *stream);
 

@@ -179,6 +179,30 @@ extern "C" int pmgk_set_mod11(double *x, int64_t first_global, int64_t n, void *
   return 0;
 }
 
+namespace {
+// out[(z * Ny + y) * Nx + x] = lx[x] * ly[y] * lz[z]: one CTA row per (z, y)
+__global__ void k_outer3(double *out, const double *__restrict__ lx, const double *__restrict__ ly, const double *__restrict__ lz,
+                         int Nx, int Ny, int nz)
+{
+  for (int row = blockIdx.x; row < Ny * nz; row += gridDim.x) {
+    const double f = ly[row % Ny] * lz[row / Ny];
+    double *o = out + (int64_t)row * Nx;
+    for (int x = threadIdx.x; x < Nx; x += blockDim.x) o[x] = f * lx[x];
+  }
+}
+} // namespace
+
+extern "C" int pmgk_outer3(double *out, const double *lx, const double *ly, const double *lz, int Nx, int Ny, int nz, void *stream)
+{
+  if (Nx <= 0 || Ny <= 0 || nz <= 0) return 0;
+  int64_t rows = (int64_t)Ny * nz;
+  const int cap = pmgk_device_sm_count() * 32;
+  if (rows > cap) rows = cap;
+  k_outer3<<<(unsigned)rows, Nx >= 192 ? 256 : (Nx >= 96 ? 128 : (Nx >= 48 ? 64 : 32)), 0, (cudaStream_t)stream>>>(out, lx, ly, lz, Nx, Ny, nz);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int pmgk_dot_work_doubles(void) { return kMaxBlocks; }
 
 extern "C" int pmgk_dot(const double *x, const double *y, int64_t n, double *result, double *work, void *stream)

@@ -223,71 +223,51 @@ int pmg_laplace_operator_assemble_rhs(const pmg_operator *op, pmg_vector *rhs)
     if (op->faces >> (2 * d) & 1u) line[d][0] = 0.0;
     if (op->faces >> (2 * d + 1) & 1u) line[d][N[d] - 1] = 0.0;
   }
-  double *host = (double *)malloc(sizeof(double) * (size_t)l->n_local);
-  if (!host) return PMG_ERR_NOMEM;
-  for (int lz = 0; lz < l->nzl; ++lz)
-    for (int y = 0; y < l->Ny; ++y) {
-      const double f = line[2][l->z0 + lz] * line[1][y];
-      double *row = host + ((int64_t)lz * l->Ny + y) * l->Nx;
-      for (int x = 0; x < l->Nx; ++x) row[x] = f * line[0][x];
-    }
-  PMG_CUDA(cudaMemcpyAsync(rhs->d, host, sizeof(double) * (size_t)l->n_local, cudaMemcpyHostToDevice, op->ctx->stream));
-  PMG_CUDA(cudaStreamSynchronize(op->ctx->stream));
-  free(host);
+  /* the load vector of f = 1 is the tensor product of the three 1-D lines: formed on the device (no O(N) host work) */
+  const size_t nl = (size_t)N[0] + N[1] + N[2];
+  double *d_lines = NULL, *h_lines = (double *)malloc(sizeof(double) * nl);
+  if (!h_lines) { for (int d = 0; d < 3; ++d) free(line[d]); return PMG_ERR_NOMEM; }
+  memcpy(h_lines, line[0], sizeof(double) * N[0]);
+  memcpy(h_lines + N[0], line[1], sizeof(double) * N[1]);
+  memcpy(h_lines + N[0] + N[1], line[2], sizeof(double) * N[2]);
   for (int d = 0; d < 3; ++d) free(line[d]);
-  return PMG_OK;
+  cudaStream_t st = op->ctx->stream;
+  int rc = PMG_OK;
+  if (cudaMallocAsync((void **)&d_lines, sizeof(double) * nl, st) != cudaSuccess ||
+      cudaMemcpyAsync(d_lines, h_lines, sizeof(double) * nl, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = PMG_ERR_CUDA;
+  if (rc == PMG_OK) rc = pmgk_outer3(rhs->d, d_lines, d_lines + N[0], d_lines + N[0] + N[1] + l->z0, l->Nx, l->Ny, l->nzl, st);
+  if (d_lines) cudaFreeAsync(d_lines, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == PMG_OK) rc = PMG_ERR_CUDA; /* h_lines is pageable */
+  free(h_lines);
+  return rc;
 }
 
-/* ||u_h||_L2 with QGauss(p+2) (program.cc:382-395), evaluated on the host from the exported vector
-   by sum factorisation cell by cell. */
+/* ||u_h||_L2 (program.cc:382-395; QGauss(p+2) there, exact for the degree-2p integrand like the (p+1)-point rule of the
+   cell mass matrix): ||u_h||^2 = u^T (Mx (x) My (x) Mz) u.  The apply kernel with the 1-D stiffness matrix replaced by
+   the mass matrix computes (cx + cy + cz) (M (x) M (x) M) u for the reference-cell M (csrc/pmg_apply_sweep.h), so the norm
+   costs one apply and one dot on the device; boundary values of u are part of the norm, hence no Dirichlet faces. */
 int pmg_laplace_operator_solution_norm(const pmg_operator *op, const pmg_vector *u, double *norm)
 {
   if (!op || !norm) return PMG_ERR_ARG;
   PMG_CHECK(check_vec(op, u, "solution_norm"));
-  const pmg_layout *l = &op->lay;
-  const int p = op->degree, n1 = p + 1, m = p + 2;
-  double *host = (double *)malloc(sizeof(double) * (size_t)l->n_global);
-  if (!host) return PMG_ERR_NOMEM;
-  PMG_CHECK(pmg_vector_export_host(u, host));
-  double gll[PMG_MAX_DEGREE + 2], g[PMG_MAX_DEGREE + 3], w[PMG_MAX_DEGREE + 3];
-  double E[(PMG_MAX_DEGREE + 3) * (PMG_MAX_DEGREE + 2)];
-  pmg_fe_gll(n1, gll);
-  pmg_fe_gauss(m, g, w);
-  for (int q = 0; q < m; ++q) pmg_fe_lagrange(n1, gll, g[q], E + q * n1, NULL);
-  const double vol = op->lv.h[0] * op->lv.h[1] * op->lv.h[2];
-  double total = 0.0;
-  double *t1 = (double *)malloc(sizeof(double) * m * n1 * n1), *t2 = (double *)malloc(sizeof(double) * m * m * n1);
-  for (int cz = 0; cz < l->nz; ++cz)
-    for (int cy = 0; cy < l->ny; ++cy)
-      for (int cx = 0; cx < l->nx; ++cx) {
-        /* x */
-        for (int k = 0; k < n1; ++k)
-          for (int j = 0; j < n1; ++j) {
-            const double *row = host + ((int64_t)(cz * p + k) * l->Ny + (cy * p + j)) * l->Nx + cx * p;
-            for (int q = 0; q < m; ++q) {
-              double s = 0.0;
-              for (int i = 0; i < n1; ++i) s += E[q * n1 + i] * row[i];
-              t1[(k * n1 + j) * m + q] = s;
-            }
-          }
-        /* y */
-        for (int k = 0; k < n1; ++k)
-          for (int qy = 0; qy < m; ++qy)
-            for (int qx = 0; qx < m; ++qx) {
-              double s = 0.0;
-              for (int j = 0; j < n1; ++j) s += E[qy * n1 + j] * t1[(k * n1 + j) * m + qx];
-              t2[(k * m + qy) * m + qx] = s;
-            }
-        /* z + accumulate */
-        for (int qz = 0; qz < m; ++qz)
-          for (int qy = 0; qy < m; ++qy)
-            for (int qx = 0; qx < m; ++qx) {
-              double s = 0.0;
-              for (int k = 0; k < n1; ++k) s += E[qz * n1 + k] * t2[(k * m + qy) * m + qx];
-              total += s * s * w[qx] * w[qy] * w[qz] * vol;
-            }
-      }
-  free(t1); free(t2); free(host);
-  *norm = sqrt(total);
+  pmg_context *ctx = op->ctx;
+  pmg_vector *t = NULL;
+  PMG_CHECK(pmg_vector_create_layout(ctx, &op->lay, &t));
+  pmgk_level lv = op->lv;
+  memcpy(lv.Kref, lv.Mref, sizeof(lv.Kref));
+  lv.faces = 0;
+  lv.tile_variant = 1; /* the line-marching kernel: the cell-tile kernel works in the eigenbasis of the (M, K) pencil */
+  int rc = PMG_OK;
+  double uMu = 0.0;
+  if (op->lay.active) {
+    rc = pmg_halo_update(ctx, &u->lay, u->d);
+    if (rc == PMG_OK) rc = pmgk_apply(&lv, PMGK_APPLY, u->d, NULL, NULL, t->d, 0.0, 0.0, ctx->stream);
+  }
+  if (rc == PMG_OK) rc = pmg_vector_dot(u, t, &uMu);
+  pmg_vector_destroy(t);
+  if (rc != PMG_OK) return rc;
+  const double *h = op->lv.h;
+  const double cx = h[1] * h[2] / h[0], cy = h[0] * h[2] / h[1], cz = h[0] * h[1] / h[2];
+  *norm = sqrt(fabs(uMu) * (h[0] * h[1] * h[2]) / (cx + cy + cz));
   return PMG_OK;
 }
