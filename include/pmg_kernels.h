@@ -34,6 +34,12 @@ typedef struct pmgk_level {
   const double *dinv_tab;  /* device, (p+2)^3 */
   const double *dinv_vec;  /* device, local vector or NULL */
   int tile_variant;        /* tuning knob: 0 = line-marching kernel (default); 2, 3 = cell-tile kernel, small/large tiles */
+  /* variable coefficient -div(a grad u) (BASELINE config 5; NULL = the reference's constant-coefficient operator):
+     w_q a(x_q) on the lexicographic grid of all quadrature points, (nx n1) x (ny n1) x ((cz_hi - coef_cz0) n1), x fastest */
+  const double *coef;
+  int coef_cz0;            /* first cell layer stored in coef (= z0 / degree) */
+  double Sq[PMGK_MAX_N1 * PMGK_MAX_N1];  /* shape values phi_i(x_q), row q (Gauss point), column i (n1 x n1) */
+  double Dco[PMGK_MAX_N1 * PMGK_MAX_N1]; /* co_shape_gradients: derivative of Gauss-point Lagrange basis r at Gauss point q */
 } pmgk_level;
 
 enum { PMGK_APPLY = 0, PMGK_RESIDUAL = 1, PMGK_CHEB_FIRST = 2, PMGK_CHEB_STEP = 3 };
@@ -44,6 +50,14 @@ int pmgk_apply(const pmgk_level *lv, int mode, const double *u, const double *b,
                double *out, double f1, double f2, void *stream);
 /* number of kernel launches pmgk_apply issues (1) and the launch geometry it would use */
 int pmgk_apply_geometry(const pmgk_level *lv, int *grid, int *block, int *smem_bytes, int *n_chunks);
+
+/* variable-coefficient set-up (csrc/pmg_apply_var.cu).  kind 1: a(x) = 1 / (0.05 + 2 |x|^2); gq / gw: HOST arrays, the
+   n1 Gauss points / weights on [0,1].  coef: device, pmgk_var_coef_doubles(lv) doubles. */
+int64_t pmgk_var_coef_doubles(const pmgk_level *lv);
+int pmgk_var_fill_coef(const pmgk_level *lv, int kind, const double *gq, const double *gw, double *coef, void *stream);
+/* inverse diagonal of the variable-coefficient operator on all stored planes (1 on constrained dofs);
+   S2 / G2: HOST n1 x n1 tables, squared shape values / squared nodal shape gradients at the Gauss points, row q */
+int pmgk_var_fill_dinv(const pmgk_level *lv, const double *S2, const double *G2, double *dinv, void *stream);
 
 /* inverse diagonal as an explicit vector (LaplaceOperator::compute_diagonal, :752-917) */
 int pmgk_fill_dinv(const pmgk_level *lv, double *dinv, void *stream);

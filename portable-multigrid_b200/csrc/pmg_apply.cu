@@ -167,10 +167,15 @@ static int launch_sweep(const pmgk_level *lv, int mode, const double *u, const d
   return 0;
 }
 
+// variable-coefficient levels: csrc/pmg_apply_var.cu
+int pmg_var_dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold, double *out,
+                     double f1, double f2, cudaStream_t s, int *geom);
+
 static int dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                     double *out, double f1, double f2, cudaStream_t s, int *geom)
 {
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
+  if (lv->coef) return pmg_var_dispatch(lv, mode, u, b, xold, out, f1, f2, s, geom);
   /* tile_variant 0 (default): the line-marching kernel for levels large enough to fill its copy pipeline, the cell-tile
      kernel (direct loads, no staging prologue) for the small coarse levels, where launch-to-result latency is everything:
      measured on B200 (tools/small_levels.py) 5.6-7.2 us against 7.0-12.3 us per fused step for Q1 up to 32^3 cells and

@@ -273,3 +273,29 @@ void pmg_fe_dinv_table(int p, const double h[3], int dim, double *tab)
         tab[tx + T * (ty + T * tz)] = 1.0 / dg;
       }
 }
+
+/* Tables of the quadrature-point formulation (variable-coefficient operator, csrc/pmg_apply_var.h), what the reference
+   reads from MatrixFree's shape_values / co_shape_gradients (include/operators/portable_laplace_operator.h:267-357):
+   Sq[q*n+i] = phi_i(x_q) (nodal GLL basis at Gauss point q), Dco[q*n+r] = derivative of the Lagrange basis ON the Gauss
+   points at Gauss point q (so grad at the quadrature points = Dco (Sq u)), G[q*n+i] = phi_i'(x_q), gq / gw = Gauss points
+   and weights on [0,1].  Any output may be NULL. */
+void pmg_fe_shape_tables(int p, double *Sq, double *Dco, double *G, double *gq, double *gw)
+{
+  const int n = p + 1;
+  double gll[NMAX], g[NMAX], w[NMAX], v[NMAX], d[NMAX];
+  pmg_fe_gll(n, gll);
+  pmg_fe_gauss(n, g, w);
+  for (int q = 0; q < n; ++q) {
+    pmg_fe_lagrange(n, gll, g[q], v, d);
+    for (int i = 0; i < n; ++i) {
+      if (Sq) Sq[q * n + i] = v[i];
+      if (G) G[q * n + i] = d[i];
+    }
+    if (Dco) {
+      pmg_fe_lagrange(n, g, g[q], NULL, d);
+      for (int r = 0; r < n; ++r) Dco[q * n + r] = d[r];
+    }
+    if (gq) gq[q] = g[q];
+    if (gw) gw[q] = w[q];
+  }
+}

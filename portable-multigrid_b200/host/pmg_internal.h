@@ -49,6 +49,7 @@ void pmg_fe_prolongation_h(int p, double *P);
 void pmg_fe_prolongation_p(int pc, int pf, double *P);
 void pmg_fe_diag_1d(int p, double *Md, double *Kd);
 void pmg_fe_dinv_table(int p, const double h[3], int dim, double *tab);
+void pmg_fe_shape_tables(int p, double *Sq, double *Dco, double *G, double *gq, double *gw);
 
 struct pmg_context {
   int device;
@@ -91,6 +92,7 @@ struct pmg_operator {
   pmg_layout lay;
   pmgk_level lv;
   double *d_dinv_tab;
+  double *d_coef;        /* variable coefficient at the quadrature points (coefficient != 0) */
   pmg_vector *dinv;      /* explicit inverse diagonal once compute_diagonal() ran */
   pmg_vector *cg_ws[4];  /* CG work vectors r, z, p, Ap: created by the first pmg_cg_solve, kept until destroy */
 };

@@ -12,13 +12,45 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Variable coefficient (BASELINE config 5; no reference equivalent): w_q a(x_q) of every quadrature point of
+   the locally stored cell layers is evaluated once on the device and streamed by the apply kernel
+   (csrc/pmg_apply_var.h); the inverse diagonal of such an operator is an explicit vector. */
+static int var_diagonal(pmg_operator *op)
+{
+  const int n1 = op->degree + 1;
+  double Sq[PMGK_MAX_N1 * PMGK_MAX_N1], G[PMGK_MAX_N1 * PMGK_MAX_N1];
+  pmg_fe_shape_tables(op->degree, Sq, NULL, G, NULL, NULL);
+  for (int i = 0; i < n1 * n1; ++i) { Sq[i] *= Sq[i]; G[i] *= G[i]; }
+  return pmgk_var_fill_dinv(&op->lv, Sq, G, op->dinv->d, op->ctx->stream);
+}
+
+static int setup_coefficient(pmg_operator *op)
+{
+  pmgk_level *lv = &op->lv;
+  double gq[PMGK_MAX_N1], gw[PMGK_MAX_N1];
+  pmg_fe_shape_tables(op->degree, lv->Sq, lv->Dco, NULL, gq, gw);
+  lv->coef_cz0 = lv->z0 / op->degree;
+  PMG_CHECK(pmg_vector_create_layout(op->ctx, &op->lay, &op->dinv));
+  if (!op->lay.active) return PMG_OK;
+  const int64_t n = pmgk_var_coef_doubles(lv);
+  if (cudaMalloc((void **)&op->d_coef, sizeof(double) * (size_t)n) != cudaSuccess) {
+    pmg_set_error("cudaMalloc of %lld coefficient values failed", (long long)n);
+    return PMG_ERR_NOMEM;
+  }
+  PMG_CHECK(pmgk_var_fill_coef(lv, op->coefficient, gq, gw, op->d_coef, op->ctx->stream));
+  lv->coef = op->d_coef;
+  PMG_CHECK(var_diagonal(op));
+  lv->dinv_vec = op->dinv->d;
+  return PMG_OK;
+}
+
 int pmg_laplace_operator_create(pmg_context *ctx, int dim, int degree, int nx, int ny, int nz,
                                 unsigned faces, int coefficient, pmg_operator **out)
 {
   if (!ctx || !out || nx < 1 || ny < 1 || nz < 1) { pmg_set_error("operator_create: bad arguments"); return PMG_ERR_ARG; }
   if (dim != 3) { pmg_set_error("only dim = 3 is compiled (the reference's 2-D driver is out of this round's scope)"); return PMG_ERR_UNSUPPORTED; }
   if (degree < 1 || degree > PMG_MAX_DEGREE) { pmg_set_error("degree %d outside 1..%d", degree, PMG_MAX_DEGREE); return PMG_ERR_UNSUPPORTED; }
-  if (coefficient != 0) { pmg_set_error("variable coefficient operator not available yet"); return PMG_ERR_UNSUPPORTED; }
+  if (coefficient != 0 && coefficient != 1) { pmg_set_error("coefficient %d: 0 = constant, 1 = 1/(0.05 + 2|x|^2)", coefficient); return PMG_ERR_UNSUPPORTED; }
   if ((int64_t)(nx * (int64_t)degree + 1) * (ny * (int64_t)degree + 1) >= (int64_t)1 << 31) return PMG_ERR_ARG;
   pmg_operator *op = (pmg_operator *)calloc(1, sizeof(*op));
   if (!op) return PMG_ERR_NOMEM;
@@ -48,6 +80,10 @@ int pmg_laplace_operator_create(pmg_context *ctx, int dim, int degree, int nx, i
   lv->dinv_vec = NULL;
   const char *tv = getenv("PMG_TILE_VARIANT");
   lv->tile_variant = tv ? atoi(tv) : 0;
+  if (coefficient != 0) {
+    const int rc = setup_coefficient(op);
+    if (rc != PMG_OK) { pmg_laplace_operator_destroy(op); return rc; }
+  }
   *out = op;
   return PMG_OK;
 }
@@ -59,6 +95,7 @@ int pmg_laplace_operator_destroy(pmg_operator *op)
   if (op->dinv) pmg_vector_destroy(op->dinv);
   for (int i = 0; i < 4; ++i) if (op->cg_ws[i]) pmg_vector_destroy(op->cg_ws[i]);
   cudaFree(op->d_dinv_tab);
+  cudaFree(op->d_coef);
   free(op);
   return PMG_OK;
 }
@@ -130,6 +167,7 @@ int pmg_laplace_operator_compute_diagonal(pmg_operator *op)
   if (!op) return PMG_ERR_ARG;
   if (!op->dinv) PMG_CHECK(pmg_vector_create_layout(op->ctx, &op->lay, &op->dinv));
   if (!op->lay.active) return PMG_OK;
+  if (op->coefficient != 0) return var_diagonal(op);
   /* diagonal of the tensor-product cell matrices summed at shared dofs, 1 on constrained dofs,
      inverted (:752-917).  The fused smoother keeps using the (p+2)^3 table: same numbers,
      no 8 B/DoF stream. */
@@ -256,6 +294,7 @@ int pmg_laplace_operator_solution_norm(const pmg_operator *op, const pmg_vector 
   pmgk_level lv = op->lv;
   memcpy(lv.Kref, lv.Mref, sizeof(lv.Kref));
   lv.faces = 0;
+  lv.coef = NULL; /* the mass matrix has no coefficient */
   lv.tile_variant = 1; /* the line-marching kernel: the cell-tile kernel works in the eigenbasis of the (M, K) pencil */
   int rc = PMG_OK;
   double uMu = 0.0;

@@ -361,11 +361,12 @@ def cg_solve(A, x, b, precond=None, max_iterations=None, tolerance=None, rel_tol
 
 
 def build_hierarchy(ctx, levels, pre=2, post=2, degree=5, smoothing_range=15.0, eig_cg_n_iterations=10,
-                    coarse_range=1e-3, faces=PMG_ALL_FACES):
+                    coarse_range=1e-3, faces=PMG_ALL_FACES, coefficient=0):
     """levels: list of (degree, n_cells) coarse -> fine; consecutive levels must be related by one
     global refinement (h) or a degree change on the same mesh (p).  Smoother parameters as in the
-    reference drivers (program.cc:267-279)."""
-    ops = [LaplaceOperator(ctx, p, n, faces) for (p, n) in levels]
+    reference drivers (program.cc:267-279).  coefficient = 1: every level discretises -div(a grad u) with
+    a = 1/(0.05 + 2|x|^2) at its own quadrature points (BASELINE config 5)."""
+    ops = [LaplaceOperator(ctx, p, n, faces, coefficient=coefficient) for (p, n) in levels]
     transfers = []
     for l in range(1, len(levels)):
         if levels[l][0] == levels[l - 1][0]:

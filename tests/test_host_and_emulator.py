@@ -207,3 +207,68 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
         assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()
         got[zol * plane:zoh * plane] = ol[owned]
     assert rel_l2(got, ref) < 1e-13
+
+
+# ---- variable-coefficient tile program (csrc/pmg_apply_var.h) under the host emulator ---------------------
+def emu_var(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, chunks=1, faces=0x3F, slab=None, dinv_vec=None,
+            want_dinv=False):
+    nx, ny, nz = n
+    h = np.array([1.0 / nx, 1.0 / ny, 1.0 / nz])
+    Nz = nz * p + 1
+    z0, nzl, czlo, czhi, zol, zoh = (0, Nz, 0, nz, 0, Nz) if slab is None else slab
+    out = np.full(u.shape, np.nan)
+    dv = np.empty(u.shape) if want_dinv else None
+    rc = emu.emu_var(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(h), mode, P(u), P(b), P(xold),
+                     P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec), P(dv))
+    assert rc == 0
+    return (out, dv) if want_dinv else out
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("small,chunks", [(1, 1), (1, 3), (0, 2)])
+def test_emulated_variable_coefficient_apply_matches_oracle(p, small, chunks, emu, oracle):
+    n = (5, 4, 3) if p < 5 else (3, 2, 3)
+    mf = oracle.MatrixFree(3, p, n, coef="c5")
+    u = splitmix_src(mf.n_dofs, salt=p)
+    out = emu_var(emu, p, n, u, small=small, chunks=chunks)
+    assert not np.isnan(out).any()
+    assert rel_l2(out, mf.vmult(u)) < 1e-13
+    const = oracle.MatrixFree(3, p, n).vmult(u)
+    assert rel_l2(out, const) > 1e-2  # the coefficient matters: not the constant-coefficient operator
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 5])
+def test_emulated_variable_coefficient_diagonal_epilogues_faces(p, emu, oracle):
+    n = (3, 4, 3) if p < 5 else (2, 3, 2)
+    mf = oracle.MatrixFree(3, p, n, coef="c5")
+    u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (21, 22, 23))
+    Au, dinv = mf.vmult(u), mf.compute_diagonal()
+    f1, f2 = 0.3, 0.8
+    out, dv = emu_var(emu, p, n, u, mode=2, b=b, f2=f2, want_dinv=True)
+    assert rel_l2(dv, dinv) < 1e-13  # diagonal by the squared-shape-function formula == e_i^T A e_i of the oracle
+    assert rel_l2(out, u + f2 * dinv * (b - Au)) < 1e-13
+    assert rel_l2(emu_var(emu, p, n, u, mode=1, b=b), b - Au) < 1e-13
+    assert rel_l2(emu_var(emu, p, n, u, mode=3, b=b, xold=xo, f1=f1, f2=f2), u + f1 * (u - xo) + f2 * dinv * (b - Au)) < 1e-13
+    for faces in (0x00, 0x2A):
+        m2 = oracle.MatrixFree(3, p, n, faces=faces, coef="c5")
+        assert rel_l2(emu_var(emu, p, n, u, faces=faces), m2.vmult(u)) < 1e-13
+
+
+@pytest.mark.parametrize("p,splits", [(1, [(0, 2), (2, 4)]), (3, [(0, 1), (1, 3), (3, 4)])])
+def test_emulated_variable_coefficient_slabs(p, splits, emu, oracle):
+    """z-slabs: each rank stores the coefficient of its own cell layers plus the ghost layer below."""
+    n = (3, 4, 4)
+    mf = oracle.MatrixFree(3, p, n, coef="c5")
+    u, b = splitmix_src(mf.n_dofs, salt=7), splitmix_src(mf.n_dofs, salt=8)
+    ref = u + 0.6 * mf.compute_diagonal() * (b - mf.vmult(u))
+    plane = mf.nd[0] * mf.nd[1]
+    got = np.full(mf.n_dofs, np.nan)
+    for lo, hi in splits:
+        z0, nzl, _, _, zol, zoh = sl = slab_of(p, n, lo, hi)
+        ul, bl = u[z0 * plane:(z0 + nzl) * plane].copy(), b[z0 * plane:(z0 + nzl) * plane].copy()
+        ol = emu_var(emu, p, n, ul, mode=2, b=bl, f2=0.6, slab=sl, chunks=2)
+        owned = np.zeros(nzl * plane, bool)
+        owned[(zol - z0) * plane:(zoh - z0) * plane] = True
+        assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()
+        got[zol * plane:zoh * plane] = ol[owned]
+    assert rel_l2(got, ref) < 1e-13

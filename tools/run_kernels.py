@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Launch the hot kernels a few times (for ncu / timing sweeps): tools/run_kernels.py DEGREE CELLS [REPS] [MODE]
-MODE: apply | cheb | both | sweep (sweep = CUDA-event timing of apply and fused Chebyshev step for degrees 1..8)."""
+MODE: apply | cheb | both | sweep (sweep = CUDA-event timing of apply and fused Chebyshev step for degrees 1..8).
+Environment: COEF=1 times the variable-coefficient operator, SWEEP_DOFS the size of the sweep (default 100e6)."""
 import os
 import sys
 
@@ -32,12 +33,13 @@ def main():
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     mode = sys.argv[4] if len(sys.argv) > 4 else "both"
     ctx = G.Context(0)
+    coef = int(os.environ.get("COEF", "0"))
     stream = torch.cuda.ExternalStream(ctx.stream())
     if mode == "sweep":
         target = float(os.environ.get("SWEEP_DOFS", "100e6"))
         for p in range(1, 9):
             n = max(2, round((target ** (1.0 / 3.0) - 1) / p))
-            op = G.LaplaceOperator(ctx, p, n)
+            op = G.LaplaceOperator(ctx, p, n, coefficient=coef)
             N = op.m()
             u, b = op.vector_from(splitmix_src(N, salt=1)), op.vector_from(splitmix_src(N, salt=2))
             z, xo = op.initialize_dof_vector(), op.initialize_dof_vector()
@@ -47,7 +49,7 @@ def main():
                   % (p, n, N, ta, N / ta / 1e6, 16 * N / ta / 1e6 / 6538.9, tc, N / tc / 1e6, 32 * N / tc / 1e6 / 6538.9), flush=True)
             del u, b, z, xo, op
         return
-    op = G.LaplaceOperator(ctx, p, n)
+    op = G.LaplaceOperator(ctx, p, n, coefficient=coef)
     N = op.m()
     u, b = op.vector_from(splitmix_src(N, salt=1)), op.vector_from(splitmix_src(N, salt=2))
     z, xo = op.initialize_dof_vector(), op.initialize_dof_vector()
