@@ -1,7 +1,6 @@
 // pmg_apply.cu -- CUDA kernels + thin C-ABI launcher for the fused Laplace apply (K1).
-// Algorithm and citations: pmg_apply_sweep.h (line-marching kernel, the default) and pmg_apply_tile.h
-// (cell-tile kernel, kept selectable for A/B measurements).  sm_100a only; there is no fallback path.
-#include "pmg_apply_sweep.h"
+// Algorithm and citations: pmg_apply_sweep.h (line-marching kernel, the default; launched from pmg_apply_sweep_m<mode>.cu),
+// pmg_apply_tile.h (cell-tile kernel: small levels) and pmg_apply_var.h (variable coefficient).  sm_100a only; there is no fallback path.
 #include "pmg_apply_tile.h"
 #include "pmg_cuda_common.h"
 #include "pmg_kernels.h"
@@ -85,87 +84,12 @@ static int launch(const pmgk_level *lv, int mode, const double *u, const double 
   return 0;
 }
 
-// ---- line-marching kernel ---------------------------------------------------------------------------
-template <class Tile>
-struct PmgSweepDeviceExec {
-  typename Tile::ThreadState st;
-  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US>
-__global__ void __launch_bounds__(NT, MINB)
-pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p)
-{
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US>;
-  extern __shared__ __align__(128) double pmg_sweep_smem[];
-  PmgSweepDeviceExec<Tile> ex;
-  const int b = blockIdx.x;
-  const int tile_x = b % p.tiles_x;
-  const int tile_y = (b / p.tiles_x) % p.tiles_y;
-  const int chunk = b / (p.tiles_x * p.tiles_y);
-  Tile::run(p, ex, pmg_sweep_smem, tile_x, tile_y, chunk);
-}
-
-// number of z-chunks: minimise waves * (layers + recomputed layer and plane below the chunk)
-static void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int *n_chunks, int *layers_per_chunk)
-{
-  double best_cost = -1;
-  int best_c = 1;
-  for (int c = 1; c <= layers; ++c) {
-    const int lpc = (layers + c - 1) / c;
-    const int used = (layers + lpc - 1) / lpc;
-    if (used != c) continue;
-    const long waves = ((long)tiles * c + slots - 1) / slots;
-    const double cost = waves * (lpc + (c > 1 ? 1.0 + 1.0 / degree : 0.0));
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
-  }
-  *n_chunks = best_c;
-  *layers_per_chunk = (layers + best_c - 1) / best_c;
-}
-
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US>
-static int launch_sweep(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
-                        double *out, double f1, double f2, cudaStream_t stream, int *geom)
-{
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US>;
-  PmgSweepParams<P> p;
-  p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
-  p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
-  p.faces = lv->faces;
-  p.z0 = lv->z0; p.nzl = lv->nzl;
-  p.cz_lo = lv->cz_lo; p.cz_hi = lv->cz_hi;
-  p.z_own_lo = lv->z_own_lo; p.z_own_hi = lv->z_own_hi;
-  p.tiles_x = (lv->nx + BX - 1) / BX;
-  p.tiles_y = (lv->ny + BY - 1) / BY;
-  // APPLY stages only u; the other modes also stage the epilogue's b / x_old rows
-  const int epi = (mode != PMGK_APPLY);
-  const int smem_bytes = Tile::smem_doubles(epi != 0) * (int)sizeof(double);
-  static int configured = 0;
-  static int ctas_per_sm[2] = {1, 1};
-  if (!configured) {
-    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Tile::SMEM_DOUBLES * (int)sizeof(double)));
-    for (int e = 0; e < 2; ++e) {
-      PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[e], pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US>, NT,
-                                                                   Tile::smem_doubles(e != 0) * sizeof(double)));
-      if (ctas_per_sm[e] < 1) return PMG_ERR_CUDA;
-    }
-    configured = 1;
-  }
-  const int slots = pmgk_device_sm_count() * ctas_per_sm[epi];
-  choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, &p.n_chunks, &p.layers_per_chunk);
-  pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
-  p.mode = mode; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
-  p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
-  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
-  if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
-  if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
-  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US><<<grid, NT, smem_bytes, stream>>>(p);
-  PMG_CUDA_CHECK(cudaGetLastError());
-  pmg_count_launch(1);
-  return 0;
-}
+// line-marching kernel, one translation unit per epilogue mode: csrc/pmg_apply_sweep_m<mode>.cu
+#define PMG_SWEEP_DECL(m) \
+  int pmg_sweep_dispatch_m##m(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, \
+                              double f2, cudaStream_t s, int *geom);
+PMG_SWEEP_DECL(0) PMG_SWEEP_DECL(1) PMG_SWEEP_DECL(2) PMG_SWEEP_DECL(3)
+#undef PMG_SWEEP_DECL
 
 // variable-coefficient levels: csrc/pmg_apply_var.cu
 int pmg_var_dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold, double *out,
@@ -184,12 +108,12 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
   const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
   const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
   if (lv->tile_variant == 1 || (lv->tile_variant == 0 && !small_level)) {
-    switch (lv->degree) {
-#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
-  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US>(lv, mode, u, b, xold, out, f1, f2, s, geom);
-#include "pmg_apply_sweep_tiles.inc"
-#undef PMG_SWEEP_CASE
-      default: return PMG_ERR_UNSUPPORTED;
+    switch (mode) { /* one kernel per epilogue mode: csrc/pmg_apply_sweep_m<mode>.cu */
+      case PMGK_APPLY: return pmg_sweep_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom);
+      case PMGK_RESIDUAL: return pmg_sweep_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom);
+      case PMGK_CHEB_FIRST: return pmg_sweep_dispatch_m2(lv, u, b, xold, out, f1, f2, s, geom);
+      case PMGK_CHEB_STEP: return pmg_sweep_dispatch_m3(lv, u, b, xold, out, f1, f2, s, geom);
+      default: return PMG_ERR_ARG;
     }
   }
 #define PMG_LAUNCH(P, BX, BY, MINB) return launch<P, BX, BY, MINB>(lv, mode, u, b, xold, out, f1, f2, s, geom)

@@ -197,9 +197,13 @@ PMG_HD constexpr int pmg_sweep_canon(int i, int j)
 // P: degree; BX x BY: cell columns per CTA; LZ: cell layers per step; NT_: threads; US: 1 = in APPLY mode every second
 // row of the u tile is fetched by the loader warp's cp.async instead of the copy engine (measured: +5 % at Q4, +2 % at Q2,
 // -4 % at Q3; in the fused modes the loader warp is busy with the b / x_old rows and the split costs 15 %)
-template <int P, int BX, int BY, int LZ, int NT_, int US = 0>
+// FM: -1 = the epilogue mode is the launch parameter p.mode; 0..3 = the kernel is compiled for that one mode and drops the
+// other three epilogue variants from its code (measured on B200, gpurun_out/exp17: apply +4 % at Q4, +10 % at Q2 / Q3,
+// +30 % at Q5 where it frees 48 registers; fused step +1..5 %)
+template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1>
 struct PmgSweepTile {
   static constexpr int N1 = P + 1;
+  static PMG_HD int mode_of(const PmgSweepParams<P> &p) { return FM >= 0 ? FM : p.mode; }
   static constexpr int NT = NT_;
   static constexpr int NPS = LZ * P;          // dof planes per step
   static constexpr int XW = (BX + 1) * P + 1; // x points of the tile: global x = (cx0-1) P + xl
@@ -273,8 +277,8 @@ struct PmgSweepTile {
     t.nxodd = p.Nx & 1; t.plodd = (p.Nx & 1) & (p.Ny & 1);
     t.eA = (int64_t)((t.cy0 - 1) * P) * p.Nx + (t.cx0 - 1) * P;
     t.n_local = (int64_t)p.Nx * p.Ny * p.nzl;
-    t.has_e = (p.mode != PMG_MODE_APPLY);
-    t.has_xo = (p.mode == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
+    t.has_e = (mode_of(p) != PMG_MODE_APPLY);
+    t.has_xo = (mode_of(p) == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
     return t;
   }
 
@@ -298,7 +302,7 @@ struct PmgSweepTile {
                           (gy == 0 && (p.faces >> 2 & 1u)) || (gy == p.Ny - 1 && (p.faces >> 3 & 1u));
         const int tx = pmg_sweep_pos_type<P>(gx, p.Nx), ty = pmg_sweep_pos_type<P>(gy, p.Ny);
         st.info[ci] = ox | (oy << 8) | (dirxy << 16) | (tx << 20) | (ty << 24);
-        if (p.mode >= PMG_MODE_CHEB_FIRST && !p.dinv_vec && !dirxy) {
+        if (mode_of(p) >= PMG_MODE_CHEB_FIRST && !p.dinv_vec && !dirxy) {
 #pragma unroll
           for (int k = 0; k < P; ++k) st.dinv[ci][k] = p.dinv_tab[tx + T * ty + T * T * k];
         }
@@ -622,7 +626,7 @@ struct PmgSweepTile {
   static PMG_HD void phase3(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *A, const double *Cb,
                             const double *Db, const double *E, int cz0, int nlay, int cz_write)
   {
-    switch (p.mode) {
+    switch (mode_of(p)) {
       case PMG_MODE_APPLY: phase3_t<PMG_MODE_APPLY>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
       case PMG_MODE_RESIDUAL: phase3_t<PMG_MODE_RESIDUAL>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
       case PMG_MODE_CHEB_FIRST: phase3_t<PMG_MODE_CHEB_FIRST>(p, t, st, A, Cb, Db, E, cz0, nlay, cz_write); break;
@@ -673,7 +677,7 @@ struct PmgSweepTile {
 
   static PMG_HD void flush(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, int gz)
   {
-    switch (p.mode) {
+    switch (mode_of(p)) {
       case PMG_MODE_APPLY: flush_t<PMG_MODE_APPLY>(p, t, st, gz); break;
       case PMG_MODE_RESIDUAL: flush_t<PMG_MODE_RESIDUAL>(p, t, st, gz); break;
       case PMG_MODE_CHEB_FIRST: flush_t<PMG_MODE_CHEB_FIRST>(p, t, st, gz); break;

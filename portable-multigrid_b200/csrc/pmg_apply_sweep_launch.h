@@ -1,0 +1,104 @@
+// pmg_apply_sweep_launch.h -- kernel entry + launcher of the line-marching apply kernel (csrc/pmg_apply_sweep.h) for ONE
+// epilogue mode.  Included by pmg_apply_sweep_m{0,1,2,3}.cu, each of which defines PMG_SWEEP_TU_MODE (the PmgApplyMode the
+// translation unit is compiled for) and so provides pmg_sweep_dispatch_m<mode>(); four translation units compile in parallel.
+#include "pmg_apply_sweep.h"
+#include "pmg_cuda_common.h"
+#include "pmg_kernels.h"
+
+namespace {
+
+template <class Tile>
+struct PmgSweepDeviceExec {
+  typename Tile::ThreadState st;
+  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>
+__global__ void __launch_bounds__(NT, MINB)
+pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p)
+{
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM>;
+  extern __shared__ __align__(128) double pmg_sweep_smem[];
+  PmgSweepDeviceExec<Tile> ex;
+  const int b = blockIdx.x;
+  const int tile_x = b % p.tiles_x;
+  const int tile_y = (b / p.tiles_x) % p.tiles_y;
+  const int chunk = b / (p.tiles_x * p.tiles_y);
+  Tile::run(p, ex, pmg_sweep_smem, tile_x, tile_y, chunk);
+}
+
+// number of z-chunks: minimise waves * (layers + recomputed layer and plane below the chunk)
+void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int *n_chunks, int *layers_per_chunk)
+{
+  double best_cost = -1;
+  int best_c = 1;
+  for (int c = 1; c <= layers; ++c) {
+    const int lpc = (layers + c - 1) / c;
+    const int used = (layers + lpc - 1) / lpc;
+    if (used != c) continue;
+    const long waves = ((long)tiles * c + slots - 1) / slots;
+    const double cost = waves * (lpc + (c > 1 ? 1.0 + 1.0 / degree : 0.0));
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+  }
+  *n_chunks = best_c;
+  *layers_per_chunk = (layers + best_c - 1) / best_c;
+}
+
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>
+int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1,
+                 double f2, cudaStream_t stream, int *geom)
+{
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM>;
+  PmgSweepParams<P> p;
+  p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
+  p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
+  p.faces = lv->faces;
+  p.z0 = lv->z0; p.nzl = lv->nzl;
+  p.cz_lo = lv->cz_lo; p.cz_hi = lv->cz_hi;
+  p.z_own_lo = lv->z_own_lo; p.z_own_hi = lv->z_own_hi;
+  p.tiles_x = (lv->nx + BX - 1) / BX;
+  p.tiles_y = (lv->ny + BY - 1) / BY;
+  // APPLY stages only u; the other modes also stage the epilogue's b / x_old rows
+  constexpr bool epi = (FM != PMG_MODE_APPLY);
+  const int smem_bytes = Tile::smem_doubles(epi) * (int)sizeof(double);
+  static int configured = 0;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem_bytes));
+    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM>, NT,
+                                                                 smem_bytes));
+    if (ctas_per_sm < 1) return PMG_ERR_CUDA;
+    configured = 1;
+  }
+  const int slots = pmgk_device_sm_count() * ctas_per_sm;
+  choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, &p.n_chunks, &p.layers_per_chunk);
+  pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
+  p.mode = FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
+  p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
+  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
+  if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
+  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM><<<grid, NT, smem_bytes, stream>>>(p);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+} // namespace
+
+#define PMG_SWEEP_CAT2(a, b) a##b
+#define PMG_SWEEP_CAT(a, b) PMG_SWEEP_CAT2(a, b)
+
+int PMG_SWEEP_CAT(pmg_sweep_dispatch_m, PMG_SWEEP_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
+                                                           double *out, double f1, double f2, cudaStream_t s, int *geom)
+{
+  switch (lv->degree) {
+#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
+  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US, PMG_SWEEP_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom);
+#include "pmg_apply_sweep_tiles.inc"
+#undef PMG_SWEEP_CASE
+    default: return PMG_ERR_UNSUPPORTED;
+  }
+}

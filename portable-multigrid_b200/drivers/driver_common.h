@@ -38,6 +38,25 @@ static int arg_int(int argc, char **argv, const char *name, int def)
   return def;
 }
 
+static double arg_double(int argc, char **argv, const char *name, double def)
+{
+  for (int i = 1; i + 1 < argc; ++i)
+    if (!strcmp(argv[i], name)) return atof(argv[i + 1]);
+  return def;
+}
+
+/* options shared by both drivers: --coefficient 1 solves -div(a grad u) = 1, a = 1/(0.05 + 2|x|^2) (BASELINE config 5),
+   --tol T the relative CG tolerance (reference 1e-12, config 5: 1e-10), --profile 1 prints the per-level device time of one
+   V-cycle (smoother / transfer / halo / other) */
+static int g_coefficient = 0, g_profile = 0;
+static double g_tol = 1e-12;
+static void common_options(int argc, char **argv)
+{
+  g_coefficient = arg_int(argc, argv, "--coefficient", 0);
+  g_profile = arg_int(argc, argv, "--profile", 0);
+  g_tol = arg_double(argc, argv, "--tol", 1e-12);
+}
+
 /* builds operators, transfers, smoothers (program.cc:203-287) and solves (:336-364); prints the reference's lines */
 static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, int post, int cheb_degree)
 {
@@ -46,7 +65,7 @@ static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, 
   pmg_chebyshev *sm[MAXL];
   memset(tr, 0, sizeof(tr));
   for (int l = 0; l < L; ++l)
-    CK(pmg_laplace_operator_create(ctx, 3, lv[l].degree, lv[l].n, lv[l].n, lv[l].n, PMG_ALL_FACES, 0, &ops[l]));
+    CK(pmg_laplace_operator_create(ctx, 3, lv[l].degree, lv[l].n, lv[l].n, lv[l].n, PMG_ALL_FACES, g_coefficient, &ops[l]));
   for (int l = 1; l < L; ++l) {
     if (lv[l].degree == lv[l - 1].degree) CK(pmg_transfer_create_geometric(ops[l - 1], ops[l], &tr[l]));
     else CK(pmg_transfer_create_polynomial(ops[l - 1], ops[l], &tr[l]));
@@ -74,7 +93,7 @@ static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, 
   int last_step = 0;
   CK(pmg_sync(ctx));
   const double t0 = now_s();
-  CK(pmg_cg_solve(A, x, rhs, mg, (int)(n_dofs > 100000 ? 100000 : n_dofs), 1e-12 * bnorm, &last_step, NULL, 0));
+  CK(pmg_cg_solve(A, x, rhs, mg, (int)(n_dofs > 100000 ? 100000 : n_dofs), g_tol * bnorm, &last_step, NULL, 0));
   CK(pmg_sync(ctx));
   const double dt = now_s() - t0;
   printf("  Solver converged in %d iterations.\n", last_step);
@@ -82,6 +101,16 @@ static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, 
   CK(pmg_laplace_operator_solution_norm(A, x, &norm));
   printf("  solution norm: %.10g\n", norm);
   printf("  [b200] solve time %.3f ms, %.3f GDoF/s (DoFs x iterations / time)\n", dt * 1e3, (double)n_dofs * last_step / dt / 1e9);
+  if (g_profile) {
+    double ms[MAXL * 4];
+    pmg_vector *z;
+    CK(pmg_laplace_operator_initialize_dof_vector(A, &z));
+    CK(pmg_vcycle_profile(mg, z, rhs, ms, MAXL));
+    printf("  [b200] one V-cycle, device ms per level (smoother / transfer / halo / other):\n");
+    for (int l = L - 1; l >= 0; --l)
+      printf("    level %2d  Q%d %4d^3 cells: %9.4f %9.4f %9.4f %9.4f\n", l, lv[l].degree, lv[l].n, ms[l * 4], ms[l * 4 + 1], ms[l * 4 + 2], ms[l * 4 + 3]);
+    pmg_vector_destroy(z);
+  }
   pmg_vector_destroy(rhs); pmg_vector_destroy(x);
   pmg_vcycle_destroy(mg);
   for (int l = 0; l < L; ++l) { pmg_chebyshev_destroy(sm[l]); if (tr[l]) pmg_transfer_destroy(tr[l]); }

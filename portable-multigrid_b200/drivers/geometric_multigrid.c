@@ -5,6 +5,7 @@
  * (:267-285, :342-343), CG to 1e-12 ||b|| (:345-352).  Prints the reference's lines (:189-199, :354-355, :395).
  * Flags: --degree D (only that degree), --max-degree M (default 7), --cycles C (default 6),
  *        --cheb-degree K (default 5; BASELINE config 1 uses 3), --pre/--post (default 2).
+ *        --coefficient 1, --tol T, --profile 1: see driver_common.h.
  */
 #include "driver_common.h"
 
@@ -32,6 +33,7 @@ int main(int argc, char **argv)
   const int cycles = arg_int(argc, argv, "--cycles", 6);
   const int cheb = arg_int(argc, argv, "--cheb-degree", 5);
   const int pre = arg_int(argc, argv, "--pre", 2), post = arg_int(argc, argv, "--post", 2);
+  common_options(argc, argv);
   pmg_context *ctx;
   CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
   for (int d = (only ? only : 1); d <= (only ? only : max_degree); ++d)

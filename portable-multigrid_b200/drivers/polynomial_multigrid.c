@@ -6,6 +6,7 @@
  * The reference program is 2-D (dim = 2, fe_degree = 7, mg_levels = 7, :439-441); the CUDA path is 3-D, so the
  * defaults here are dim = 3, fe_degree = 4, mg_levels = 4, cycles = 5.
  * --hp 1 selects BASELINE config 2 instead: p = 4 -> 2 -> 1 followed by geometric levels.
+ * --coefficient 1, --tol T, --profile 1: see driver_common.h (BASELINE config 5: --hp 1 --degree 5 --coefficient 1 --tol 1e-10).
  */
 #include "driver_common.h"
 
@@ -18,6 +19,7 @@ int main(int argc, char **argv)
   const int hp = arg_int(argc, argv, "--hp", 0);
   const int pre = arg_int(argc, argv, "--pre", 2), post = arg_int(argc, argv, "--post", 2);
   if (mg_levels > fe_degree) mg_levels = fe_degree; /* Assert(mg_levels <= fe_degree) (:140-142) */
+  common_options(argc, argv);
   pmg_context *ctx;
   CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
   for (int cycle = 0; cycle < cycles; ++cycle) {

@@ -12,7 +12,10 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #ifndef C_US
 #define C_US 0
 #endif
-#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US
+#ifndef C_FM
+#define C_FM -1
+#endif
+#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM
 #define STR2(x) #x
 #define STR(x) STR2(x)
 #define CFGSTR STR(C_P) "," STR(C_BX) "," STR(C_BY) "," STR(C_LZ) "," STR(C_NT)
@@ -23,7 +26,18 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 using Tile = PmgSweepTile<CFG>;
 struct Ex {
   Tile::ThreadState st;
+#ifdef PMG_EXP_ROT
+  // rotate the warps' roles from CTA to CTA: the CTAs resident on one SM (b, b + 148, b + 296 in the first wave) then put
+  // their busy warps (phases 1 / 2 occupy the first ones) on different SM sub-partitions
+  template <class F> __device__ __forceinline__ void for_each_thread(F f)
+  {
+    constexpr int NW = Tile::NT / 32;
+    const int rot = (blockIdx.x / 148 + blockIdx.x) % NW;
+    f((int)((((threadIdx.x >> 5) + rot) % NW) * 32 + (threadIdx.x & 31)), st);
+  }
+#else
   template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
+#endif
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 __global__ void __launch_bounds__(Tile::NT, MINB) kern(const __grid_constant__ PmgSweepParams<PP> p)
@@ -69,7 +83,11 @@ int main(int argc, char **argv)
   p.layers_per_chunk = (n + chunks - 1) / chunks; p.n_chunks = (n + p.layers_per_chunk - 1) / p.layers_per_chunk;
   const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+#if C_FM >= 0
+  for (int mode : {C_FM}) {
+#else
   for (int mode : {0, 3}) {
+#endif
     p.mode = mode; p.out = (mode == 3) ? xo : out;
     smem = Tile::smem_doubles(mode != 0) * 8;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Tile::NT, smem));
