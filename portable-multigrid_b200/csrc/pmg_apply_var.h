@@ -85,6 +85,21 @@ PMG_HD double pmg_var_diag_entry(int gx, int gy, int gz, int nx, int ny, int cz_
   return diag;
 }
 
+// hint: bring the line at `ptr` closer (L2, or L1 with PMG_VAR_PREFETCH_L1); the kernel's global loads are consumed right
+// where they are issued, two to three barriers after the place where their addresses are known
+PMG_HD void pmg_var_prefetch(const double *ptr)
+{
+#if defined(__CUDA_ARCH__)
+#ifdef PMG_VAR_PREFETCH_L1
+  asm volatile("prefetch.global.L1 [%0];\n" ::"l"(ptr));
+#else
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+#endif
+#else
+  (void)ptr;
+#endif
+}
+
 template <int P, int BX, int BY>
 struct PmgVarTile {
   using Base = PmgApplyTile<P, BX, BY>;
@@ -148,6 +163,7 @@ struct PmgVarTile {
     const int Qx = p.nx * N1;
     const int64_t Qplane = (int64_t)Qx * (p.ny * N1);
     const double *cw = p.coef + (int64_t)(cz - p.coef_cz0) * N1 * Qplane + (int64_t)(st.cy * N1 + st.j) * Qx + st.cx * N1;
+#ifdef PMG_VAR_XZ_REGS
     double U[N1][N1], R[N1][N1];
 #pragma unroll
     for (int m = 0; m < N1; ++m)
@@ -182,6 +198,49 @@ struct PmgVarTile {
 #pragma unroll
         for (int a = 0; a < N1; ++a) R[r][a] += p.D[m * N1 + r] * gz[a];
     }
+#else
+    // R stays in registers; U is read from T1 where it is needed (row m for the x derivative, all rows for the z
+    // derivative): (P+1)^3 shared-memory loads per thread against 4 (P+1)^3 FMAs, and half the registers of holding both
+    double R[N1][N1];
+#pragma unroll
+    for (int m = 0; m < N1; ++m)
+#pragma unroll
+      for (int a = 0; a < N1; ++a) R[m][a] = 0.0;
+#pragma unroll
+    for (int m = 0; m < N1; ++m) {
+      double w[N1], gx[N1], gz[N1], Um[N1];
+#pragma unroll
+      for (int a = 0; a < N1; ++a) { w[a] = cw[m * Qplane + a]; Um[a] = t1[m * MSTRIDE + a]; gz[a] = 0.0; }
+#pragma unroll
+      for (int a = 0; a < N1; ++a) t2[m * MSTRIDE + a] *= p.c[1] * w[a];
+      // derivatives at the quadrature points (a, b, m), a = 0..P
+#pragma unroll
+      for (int r = 0; r < N1; ++r) {
+#pragma unroll
+        for (int a = 0; a < N1; ++a) gz[a] += p.D[m * N1 + r] * t1[r * MSTRIDE + a];
+      }
+#pragma unroll
+      for (int a = 0; a < N1; ++a) {
+        double sx = 0.0;
+#pragma unroll
+        for (int r = 0; r < N1; ++r) sx += p.D[a * N1 + r] * Um[r];
+        gx[a] = sx * (p.c[0] * w[a]);
+        gz[a] *= p.c[2] * w[a];
+      }
+      // transposed derivatives
+#pragma unroll
+      for (int r = 0; r < N1; ++r) {
+        double s = R[m][r];
+#pragma unroll
+        for (int a = 0; a < N1; ++a) s += p.D[a * N1 + r] * gx[a];
+        R[m][r] = s;
+      }
+#pragma unroll
+      for (int r = 0; r < N1; ++r)
+#pragma unroll
+        for (int a = 0; a < N1; ++a) R[r][a] += p.D[m * N1 + r] * gz[a];
+    }
+#endif
 #pragma unroll
     for (int m = 0; m < N1; ++m)
 #pragma unroll
@@ -217,6 +276,30 @@ struct PmgVarTile {
     }
   }
 
+  // thread (cell, j): prefetch the coefficient rows phase XZ of layer cz will read and the u rows phase F of layer
+  // cz + 1 will read (a row = P+1 consecutive doubles: one or two 32-byte sectors)
+  static PMG_HD void prefetch_layer(const PmgVarParams<P> &p, const ThreadState &st, int cz, bool next_u)
+  {
+    if (!st.valid) return;
+    const int Qx = p.nx * N1;
+    const int64_t Qplane = (int64_t)Qx * (p.ny * N1);
+    const double *cw = p.coef + (int64_t)(cz - p.coef_cz0) * N1 * Qplane + (int64_t)(st.cy * N1 + st.j) * Qx + st.cx * N1;
+#pragma unroll
+    for (int m = 0; m < N1; ++m) {
+      pmg_var_prefetch(cw + m * Qplane);
+      if (N1 > 4) pmg_var_prefetch(cw + m * Qplane + P);
+    }
+    if (next_u) {
+      const int64_t plane = (int64_t)p.Nx * p.Ny;
+      const double *row = p.u + (int64_t)((cz + 1) * P - p.z0) * plane + (int64_t)(st.cy * P + st.j) * p.Nx + st.cx * P;
+#pragma unroll
+      for (int k = 1; k < N1; ++k) {
+        pmg_var_prefetch(row + k * plane);
+        if (N1 > 4) pmg_var_prefetch(row + k * plane + P);
+      }
+    }
+  }
+
   template <class Exec>
   static PMG_HD void run(const PmgVarParams<P> &p, Exec &ex, double *smem, int tile_x, int tile_y, int chunk)
   {
@@ -235,7 +318,12 @@ struct PmgVarTile {
       const bool write_out = (cz >= cz_begin);
       // T1 was last read by the previous layer's B phase, O (= T2) by its epilogue: F writes T1 only, and the barrier
       // after F orders the epilogue's reads of O before Y1's writes to T2
-      ex.for_each_thread([&](int, ThreadState &st) { Base::phase_forward(p, st, smem, cz, first); });
+      ex.for_each_thread([&](int, ThreadState &st) {
+#ifndef PMG_VAR_NO_PREFETCH
+        prefetch_layer(p, st, cz, cz + 1 < cz_end);
+#endif
+        Base::phase_forward(p, st, smem, cz, first);
+      });
       ex.sync();
       ex.for_each_thread([&](int tid, ThreadState &) { phase_y1(p, tid, cx0, cy0, smem); });
       ex.sync();
