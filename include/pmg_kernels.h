@@ -19,6 +19,7 @@ extern "C" {
 
 /* One multigrid level as the kernels see it (structured box, lexicographic dofs). */
 typedef struct pmgk_level {
+  int dim;               /* 3, or 2: one dof plane (Nz = 1, nz = 1 as a placeholder), faces bits 0..3, kernels of csrc/pmg_dim2.cu */
   int degree;
   int nx, ny, nz;        /* global cells */
   int Nx, Ny, Nz;        /* global dofs per direction */

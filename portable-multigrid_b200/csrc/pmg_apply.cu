@@ -91,6 +91,10 @@ static int launch(const pmgk_level *lv, int mode, const double *u, const double 
 PMG_SWEEP_DECL(0) PMG_SWEEP_DECL(1) PMG_SWEEP_DECL(2) PMG_SWEEP_DECL(3)
 #undef PMG_SWEEP_DECL
 
+// 2-D levels: csrc/pmg_dim2.cu
+int pmg_dim2_apply(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold, double *out, double f1,
+                   double f2, cudaStream_t s, int *geom);
+
 // variable-coefficient levels: csrc/pmg_apply_var.cu
 int pmg_var_dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold, double *out,
                      double f1, double f2, cudaStream_t s, int *geom);
@@ -98,6 +102,7 @@ int pmg_var_dispatch(const pmgk_level *lv, int mode, const double *u, const doub
 static int dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                     double *out, double f1, double f2, cudaStream_t s, int *geom)
 {
+  if (lv->dim == 2) return pmg_dim2_apply(lv, mode, u, b, xold, out, f1, f2, s, geom);
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
   if (lv->coef) return pmg_var_dispatch(lv, mode, u, b, xold, out, f1, f2, s, geom);
   /* tile_variant 0 (default): the line-marching kernel for levels large enough to fill its copy pipeline, the cell-tile

@@ -397,9 +397,14 @@ int pick_cpb(int NC, int NF)
 
 } // namespace
 
+// 2-D levels: csrc/pmg_dim2.cu
+int pmg_dim2_prolongate(int kind, const pmgk_level *c, const pmgk_level *f, const double *P1d, double *dst, const double *src, cudaStream_t s);
+int pmg_dim2_restrict(int kind, const pmgk_level *c, const pmgk_level *f, const double *P1d, double *dst, const double *src, cudaStream_t s);
+
 extern "C" int64_t pmgk_restrict_scratch_doubles(int kind, const pmgk_level *coarse, const pmgk_level *fine)
 {
   (void)kind; (void)fine;
+  if (coarse->dim == 2) return 0; /* gather per coarse dof, no cell-local scratch */
   const int NC = coarse->degree + 1;
   return (int64_t)coarse->nx * coarse->ny * (coarse->cz_hi - coarse->cz_lo) * NC * NC * NC;
 }
@@ -495,6 +500,7 @@ static int dispatch_restrict(const XferGeom &g, const double *P1d, double *scrat
 extern "C" int pmgk_prolongate_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
                                        double *dst_fine, const double *src_coarse, void *stream)
 {
+  if (coarse->dim == 2) return pmg_dim2_prolongate(kind, coarse, fine, P1d, dst_fine, src_coarse, (cudaStream_t)stream);
   XferGeom g;
   const int rc = make_geom(kind, coarse, fine, &g);
   if (rc) return rc;
@@ -505,6 +511,7 @@ extern "C" int pmgk_prolongate_and_add(int kind, const pmgk_level *coarse, const
 extern "C" int pmgk_restrict_and_add(int kind, const pmgk_level *coarse, const pmgk_level *fine, const double *P1d,
                                      double *dst_coarse, const double *src_fine, double *scratch, void *stream)
 {
+  if (coarse->dim == 2) return pmg_dim2_restrict(kind, coarse, fine, P1d, dst_coarse, src_fine, (cudaStream_t)stream);
   XferGeom g;
   int rc = make_geom(kind, coarse, fine, &g);
   if (rc) return rc;

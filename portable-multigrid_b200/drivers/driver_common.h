@@ -48,13 +48,20 @@ static double arg_double(int argc, char **argv, const char *name, double def)
 /* options shared by both drivers: --coefficient 1 solves -div(a grad u) = 1, a = 1/(0.05 + 2|x|^2) (BASELINE config 5),
    --tol T the relative CG tolerance (reference 1e-12, config 5: 1e-10), --profile 1 prints the per-level device time of one
    V-cycle (smoother / transfer / halo / other) */
-static int g_coefficient = 0, g_profile = 0;
+static int g_coefficient = 0, g_profile = 0, g_dim = 3;
 static double g_tol = 1e-12;
 static void common_options(int argc, char **argv)
 {
   g_coefficient = arg_int(argc, argv, "--coefficient", 0);
   g_profile = arg_int(argc, argv, "--profile", 0);
   g_tol = arg_double(argc, argv, "--tol", 1e-12);
+}
+
+static long long n_dofs_of(int degree, int n)
+{
+  long long r = 1;
+  for (int d = 0; d < g_dim; ++d) r *= (long long)n * degree + 1;
+  return r;
 }
 
 /* builds operators, transfers, smoothers (program.cc:203-287) and solves (:336-364); prints the reference's lines */
@@ -65,7 +72,7 @@ static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, 
   pmg_chebyshev *sm[MAXL];
   memset(tr, 0, sizeof(tr));
   for (int l = 0; l < L; ++l)
-    CK(pmg_laplace_operator_create(ctx, 3, lv[l].degree, lv[l].n, lv[l].n, lv[l].n, PMG_ALL_FACES, g_coefficient, &ops[l]));
+    CK(pmg_laplace_operator_create(ctx, g_dim, lv[l].degree, lv[l].n, lv[l].n, lv[l].n, PMG_ALL_FACES, g_coefficient, &ops[l]));
   for (int l = 1; l < L; ++l) {
     if (lv[l].degree == lv[l - 1].degree) CK(pmg_transfer_create_geometric(ops[l - 1], ops[l], &tr[l]));
     else CK(pmg_transfer_create_polynomial(ops[l - 1], ops[l], &tr[l]));
@@ -108,7 +115,7 @@ static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, 
     CK(pmg_vcycle_profile(mg, z, rhs, ms, MAXL));
     printf("  [b200] one V-cycle, device ms per level (smoother / transfer / halo / other):\n");
     for (int l = L - 1; l >= 0; --l)
-      printf("    level %2d  Q%d %4d^3 cells: %9.4f %9.4f %9.4f %9.4f\n", l, lv[l].degree, lv[l].n, ms[l * 4], ms[l * 4 + 1], ms[l * 4 + 2], ms[l * 4 + 3]);
+      printf("    level %2d  Q%d %4d^d cells: %9.4f %9.4f %9.4f %9.4f\n", l, lv[l].degree, lv[l].n, ms[l * 4], ms[l * 4 + 1], ms[l * 4 + 2], ms[l * 4 + 3]);
     pmg_vector_destroy(z);
   }
   pmg_vector_destroy(rhs); pmg_vector_destroy(x);

@@ -5,7 +5,7 @@
  * (:267-285, :342-343), CG to 1e-12 ||b|| (:345-352).  Prints the reference's lines (:189-199, :354-355, :395).
  * Flags: --degree D (only that degree), --max-degree M (default 7), --cycles C (default 6),
  *        --cheb-degree K (default 5; BASELINE config 1 uses 3), --pre/--post (default 2).
- *        --coefficient 1, --tol T, --profile 1: see driver_common.h.
+ *        --coefficient 1, --tol T, --profile 1: see driver_common.h; --dim 2 runs the unit square (reference: dim = 3, :470).
  */
 #include "driver_common.h"
 
@@ -17,8 +17,8 @@ static int run_degree(pmg_context *ctx, int degree, int cycles, int pre, int pos
     level_t lv[MAXL];
     const int L = cycle + 1; /* create_geometric_coarsening_sequence: 1, 2, 4, ... cells per direction */
     for (int l = 0; l < L; ++l) { lv[l].degree = degree; lv[l].n = 1 << l; }
-    printf(" Number of degrees of freedom: %lld (by level: ", (long long)pow((double)lv[L - 1].n * degree + 1, 3));
-    for (int l = 0; l < L; ++l) printf("%lld%s", (long long)pow((double)lv[l].n * degree + 1, 3), l == L - 1 ? ")" : ", ");
+    printf(" Number of degrees of freedom: %lld (by level: ", n_dofs_of(degree, lv[L - 1].n));
+    for (int l = 0; l < L; ++l) printf("%lld%s", n_dofs_of(degree, lv[l].n), l == L - 1 ? ")" : ", ");
     printf("\n");
     if (solve_hierarchy(ctx, lv, L, pre, post, cheb)) return 1;
     printf("\n");
@@ -34,6 +34,7 @@ int main(int argc, char **argv)
   const int cheb = arg_int(argc, argv, "--cheb-degree", 5);
   const int pre = arg_int(argc, argv, "--pre", 2), post = arg_int(argc, argv, "--post", 2);
   common_options(argc, argv);
+  g_dim = arg_int(argc, argv, "--dim", 3);
   pmg_context *ctx;
   CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
   for (int d = (only ? only : 1); d <= (only ? only : max_degree); ++d)

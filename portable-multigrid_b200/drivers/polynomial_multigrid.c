@@ -3,8 +3,8 @@
  * on top of the C-ABI: p-multigrid with levels p = fe_degree-(mg_levels-1) .. fe_degree on one mesh
  * (program.cc:144-158, p -> p-1 transfers :241-242), V(2,2), Chebyshev(5)-Jacobi, coarsest level smoothed to
  * 1e-3 with eig_cg_n_iterations = m() (:320-336), CG to 1e-12 ||b|| (:346-353).
- * The reference program is 2-D (dim = 2, fe_degree = 7, mg_levels = 7, :439-441); the CUDA path is 3-D, so the
- * defaults here are dim = 3, fe_degree = 4, mg_levels = 4, cycles = 5.
+ * Defaults = the reference program (:439-441, :399): dim = 2, fe_degree = 7, mg_levels = 7, seven refinement cycles
+ * (1 .. 64^2 cells).  --dim 3 runs the same hierarchy on the unit cube (then think of --degree 4 --cycles 5).
  * --hp 1 selects BASELINE config 2 instead: p = 4 -> 2 -> 1 followed by geometric levels.
  * --coefficient 1, --tol T, --profile 1: see driver_common.h (BASELINE config 5: --hp 1 --degree 5 --coefficient 1 --tol 1e-10).
  */
@@ -12,14 +12,15 @@
 
 int main(int argc, char **argv)
 {
-  const int fe_degree = arg_int(argc, argv, "--degree", 4);
+  const int fe_degree = arg_int(argc, argv, "--degree", 7);
   int mg_levels = arg_int(argc, argv, "--levels", fe_degree);
-  const int cycles = arg_int(argc, argv, "--cycles", 5);
+  const int cycles = arg_int(argc, argv, "--cycles", 7);
   const int cheb = arg_int(argc, argv, "--cheb-degree", 5);
   const int hp = arg_int(argc, argv, "--hp", 0);
   const int pre = arg_int(argc, argv, "--pre", 2), post = arg_int(argc, argv, "--post", 2);
   if (mg_levels > fe_degree) mg_levels = fe_degree; /* Assert(mg_levels <= fe_degree) (:140-142) */
   common_options(argc, argv);
+  g_dim = arg_int(argc, argv, "--dim", 2);
   pmg_context *ctx;
   CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
   for (int cycle = 0; cycle < cycles; ++cycle) {
@@ -38,7 +39,7 @@ int main(int argc, char **argv)
       for (int l = 0; l < mg_levels; ++l) { lv[L].degree = fe_degree - (mg_levels - 1 - l); lv[L].n = n; ++L; }
     }
     for (int l = 0; l < L; ++l)
-      printf("level %d: p = %d, DoFs = %lld\n", l, lv[l].degree, (long long)pow((double)lv[l].n * lv[l].degree + 1, 3));
+      printf("level %d: p = %d, DoFs = %lld\n", l, lv[l].degree, n_dofs_of(lv[l].degree, lv[l].n));
     if (solve_hierarchy(ctx, lv, L, pre, post, cheb)) return 1;
     printf("\n");
   }

@@ -142,18 +142,19 @@ int pmg_host_partition(int nz, int n_ranks, int rank, int *cz_lo, int *cz_hi)
   return PMG_OK;
 }
 
-int pmg_layout_make(pmg_context *ctx, int degree, int nx, int ny, int nz, pmg_layout *lay)
+int pmg_layout_make(pmg_context *ctx, int dim, int degree, int nx, int ny, int nz, pmg_layout *lay)
 {
   memset(lay, 0, sizeof(*lay));
+  if (dim == 2) nz = 1; /* 2-D: a single dof plane; nz = 1 is a placeholder, the level is never cut into slabs */
   lay->nx = nx; lay->ny = ny; lay->nz = nz; lay->degree = degree;
-  lay->Nx = nx * degree + 1; lay->Ny = ny * degree + 1; lay->Nz = nz * degree + 1;
+  lay->Nx = nx * degree + 1; lay->Ny = ny * degree + 1; lay->Nz = (dim == 2) ? 1 : nz * degree + 1;
   lay->plane = (int64_t)lay->Nx * lay->Ny;
   lay->n_global = lay->plane * lay->Nz;
   lay->lower = lay->upper = -1;
   const int R = ctx->n_ranks, r = ctx->rank;
   int cz_lo = 0, cz_hi = nz;
   int distributed = 0;
-  if (R > 1 && lay->n_global >= ctx->coarse_threshold) {
+  if (R > 1 && dim == 3 && lay->n_global >= ctx->coarse_threshold) {
     const int rc = pmg_host_partition(nz, R, r, &cz_lo, &cz_hi);
     if (rc < 0) return rc;
     distributed = (rc == 0);

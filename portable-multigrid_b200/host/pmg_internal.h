@@ -116,7 +116,7 @@ struct pmg_chebyshev {
   pmg_vector *t0, *t1;   /* ping-pong work vectors */
 };
 
-int pmg_layout_make(pmg_context *ctx, int degree, int nx, int ny, int nz, pmg_layout *lay);
+int pmg_layout_make(pmg_context *ctx, int dim, int degree, int nx, int ny, int nz, pmg_layout *lay);
 int pmg_layout_same(const pmg_layout *a, const pmg_layout *b);
 int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector **v);
 int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d);

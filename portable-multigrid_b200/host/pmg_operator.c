@@ -48,15 +48,18 @@ int pmg_laplace_operator_create(pmg_context *ctx, int dim, int degree, int nx, i
                                 unsigned faces, int coefficient, pmg_operator **out)
 {
   if (!ctx || !out || nx < 1 || ny < 1 || nz < 1) { pmg_set_error("operator_create: bad arguments"); return PMG_ERR_ARG; }
-  if (dim != 3) { pmg_set_error("only dim = 3 is compiled (the reference's 2-D driver is out of this round's scope)"); return PMG_ERR_UNSUPPORTED; }
+  if (dim != 2 && dim != 3) { pmg_set_error("dim = %d: the reference instantiates dim = 2 and dim = 3", dim); return PMG_ERR_UNSUPPORTED; }
+  if (dim == 2) { nz = 1; faces &= 0xFu; }
+  if (dim == 2 && coefficient != 0) { pmg_set_error("the variable-coefficient operator is 3-D only"); return PMG_ERR_UNSUPPORTED; }
   if (degree < 1 || degree > PMG_MAX_DEGREE) { pmg_set_error("degree %d outside 1..%d", degree, PMG_MAX_DEGREE); return PMG_ERR_UNSUPPORTED; }
   if (coefficient != 0 && coefficient != 1) { pmg_set_error("coefficient %d: 0 = constant, 1 = 1/(0.05 + 2|x|^2)", coefficient); return PMG_ERR_UNSUPPORTED; }
   if ((int64_t)(nx * (int64_t)degree + 1) * (ny * (int64_t)degree + 1) >= (int64_t)1 << 31) return PMG_ERR_ARG;
   pmg_operator *op = (pmg_operator *)calloc(1, sizeof(*op));
   if (!op) return PMG_ERR_NOMEM;
   op->ctx = ctx; op->dim = dim; op->degree = degree; op->coefficient = coefficient; op->faces = faces & PMG_ALL_FACES;
-  PMG_CHECK(pmg_layout_make(ctx, degree, nx, ny, nz, &op->lay));
+  PMG_CHECK(pmg_layout_make(ctx, dim, degree, nx, ny, nz, &op->lay));
   pmgk_level *lv = &op->lv;
+  lv->dim = dim;
   lv->degree = degree;
   lv->nx = nx; lv->ny = ny; lv->nz = nz;
   lv->Nx = op->lay.Nx; lv->Ny = op->lay.Ny; lv->Nz = op->lay.Nz;
@@ -64,7 +67,7 @@ int pmg_laplace_operator_create(pmg_context *ctx, int dim, int degree, int nx, i
   lv->z0 = op->lay.z0; lv->nzl = op->lay.nzl;
   lv->cz_lo = op->lay.cz_lo; lv->cz_hi = op->lay.cz_hi;
   lv->z_own_lo = op->lay.z_own_lo; lv->z_own_hi = op->lay.z_own_hi;
-  lv->h[0] = 1.0 / nx; lv->h[1] = 1.0 / ny; lv->h[2] = 1.0 / nz;
+  lv->h[0] = 1.0 / nx; lv->h[1] = 1.0 / ny; lv->h[2] = (dim == 2) ? 1.0 : 1.0 / nz;
   pmg_fe_fastdiag(degree, lv->S, lv->lam);
   pmg_fe_pencil(degree, lv->Mref, lv->Kref);
   const int T = degree + 2;
@@ -256,6 +259,7 @@ int pmg_laplace_operator_assemble_rhs(const pmg_operator *op, pmg_vector *rhs)
   for (int d = 0; d < 3; ++d) {
     line[d] = (double *)calloc((size_t)N[d], sizeof(double));
     if (!line[d]) return PMG_ERR_NOMEM;
+    if (d == 2 && op->dim == 2) { line[d][0] = 1.0; continue; } /* 2-D: the single plane */
     for (int c = 0; c < nc[d]; ++c)
       for (int i = 0; i < n1; ++i) line[d][c * p + i] += b1[i] * op->lv.h[d];
     if (op->faces >> (2 * d) & 1u) line[d][0] = 0.0;
@@ -306,6 +310,10 @@ int pmg_laplace_operator_solution_norm(const pmg_operator *op, const pmg_vector 
   pmg_vector_destroy(t);
   if (rc != PMG_OK) return rc;
   const double *h = op->lv.h;
+  if (op->dim == 2) { /* the 2-D apply computes (hy/hx + hx/hy) (M (x) M) u */
+    *norm = sqrt(fabs(uMu) * (h[0] * h[1]) / (h[1] / h[0] + h[0] / h[1]));
+    return PMG_OK;
+  }
   const double cx = h[1] * h[2] / h[0], cy = h[0] * h[2] / h[1], cz = h[0] * h[1] / h[2];
   *norm = sqrt(fabs(uMu) * (h[0] * h[1] * h[2]) / (cx + cy + cz));
   return PMG_OK;

@@ -25,7 +25,7 @@ static int transfer_create(int kind, const pmg_operator *coarse, const pmg_opera
   const pmg_layout *c = &coarse->lay, *f = &fine->lay;
   if (coarse->faces != fine->faces || coarse->dim != fine->dim) { pmg_set_error("transfer: levels differ in boundary description"); return PMG_ERR_ARG; }
   if (kind == 0) {
-    if (coarse->degree != fine->degree || f->nx != 2 * c->nx || f->ny != 2 * c->ny || f->nz != 2 * c->nz) {
+    if (coarse->degree != fine->degree || f->nx != 2 * c->nx || f->ny != 2 * c->ny || (coarse->dim == 3 && f->nz != 2 * c->nz)) {
       pmg_set_error("geometric transfer: fine mesh is not the coarse mesh refined once (reference AssertThrow, portable_geometric_transfer.h:1055)");
       return PMG_ERR_ARG;
     }

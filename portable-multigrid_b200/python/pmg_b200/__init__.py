@@ -181,8 +181,9 @@ class LaplaceOperator:
 
     def __init__(self, ctx, degree, n, dirichlet_faces=PMG_ALL_FACES, dim=3, coefficient=0):
         if isinstance(n, int):
-            n = (n, n, n)
-        self.ctx, self.degree, self.ncells = ctx, degree, tuple(n)
+            n = (n,) * dim
+        n = tuple(n) + (1,) * (3 - len(n))  # dim = 2: (nx, ny); the C-ABI ignores nz
+        self.ctx, self.degree, self.ncells, self.dim = ctx, degree, tuple(n), dim
         self.h = _vp()
         _ck(lib().pmg_laplace_operator_create(ctx.h, C.c_int(dim), C.c_int(degree), C.c_int(n[0]), C.c_int(n[1]),
                                               C.c_int(n[2]), C.c_uint(dirichlet_faces), C.c_int(coefficient), C.byref(self.h)))
@@ -361,12 +362,12 @@ def cg_solve(A, x, b, precond=None, max_iterations=None, tolerance=None, rel_tol
 
 
 def build_hierarchy(ctx, levels, pre=2, post=2, degree=5, smoothing_range=15.0, eig_cg_n_iterations=10,
-                    coarse_range=1e-3, faces=PMG_ALL_FACES, coefficient=0):
+                    coarse_range=1e-3, faces=PMG_ALL_FACES, coefficient=0, dim=3):
     """levels: list of (degree, n_cells) coarse -> fine; consecutive levels must be related by one
     global refinement (h) or a degree change on the same mesh (p).  Smoother parameters as in the
     reference drivers (program.cc:267-279).  coefficient = 1: every level discretises -div(a grad u) with
     a = 1/(0.05 + 2|x|^2) at its own quadrature points (BASELINE config 5)."""
-    ops = [LaplaceOperator(ctx, p, n, faces, coefficient=coefficient) for (p, n) in levels]
+    ops = [LaplaceOperator(ctx, p, n, faces, dim=dim, coefficient=coefficient) for (p, n) in levels]
     transfers = []
     for l in range(1, len(levels)):
         if levels[l][0] == levels[l - 1][0]:

@@ -287,4 +287,6 @@ def test_error_paths(pmg, ctx):
     with pytest.raises(pmg.PmgError):
         va.add(1.0, vb)
     with pytest.raises(pmg.PmgError):
-        pmg.LaplaceOperator(ctx, 2, 4, dim=2)
+        pmg.LaplaceOperator(ctx, 2, 4, dim=4)
+    with pytest.raises(pmg.PmgError):
+        pmg.LaplaceOperator(ctx, 2, 4, dim=2, coefficient=1)  # the coefficient extension is 3-D only

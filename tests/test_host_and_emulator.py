@@ -272,3 +272,45 @@ def test_emulated_variable_coefficient_slabs(p, splits, emu, oracle):
         assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()
         got[zol * plane:zoh * plane] = ol[owned]
     assert rel_l2(got, ref) < 1e-13
+
+
+# ---- the 2-D kernels' per-DoF functions (csrc/pmg_dim2.h) under the host emulator ----------------------------------
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("faces", [0xF, 0x5, 0x0])
+def test_emulated_2d_apply_and_epilogues(p, faces, emu, oracle):
+    n = (5, 3) if p < 5 else (3, 2)
+    mf = oracle.MatrixFree(2, p, n, faces=faces)
+    u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (41, 42, 43))
+    Au, dinv = mf.vmult(u), mf.compute_diagonal()
+
+    def run(mode, f1=0.0, f2=0.0, xold=None, dinv_vec=None, out=None):
+        out = np.empty(mf.n_dofs) if out is None else out
+        assert emu.emu2_apply(p, n[0], n[1], C.c_uint(faces), mode, P(u), P(b), P(xold), P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec)) == 0
+        return out
+
+    assert rel_l2(run(0), Au) < 1e-13
+    assert np.array_equal(run(0)[mf.constrained()], u[mf.constrained()])
+    assert rel_l2(run(1), b - Au) < 1e-13
+    assert rel_l2(run(2, f2=0.7), u + 0.7 * dinv * (b - Au)) < 1e-13
+    ref = u + 0.3 * (u - xo) + 0.7 * dinv * (b - Au)
+    assert rel_l2(run(3, 0.3, 0.7, xold=xo), ref) < 1e-13
+    assert rel_l2(run(3, 0.3, 0.7, xold=xo, dinv_vec=dinv), ref) < 1e-13
+    x2 = xo.copy()
+    run(3, 0.3, 0.7, xold=x2, out=x2)  # x_old overwritten in place
+    assert rel_l2(x2, ref) < 1e-13
+
+
+@pytest.mark.parametrize("kind,pc,pf,n", [("h", 1, 1, (3, 2)), ("h", 2, 2, (3, 2)), ("h", 3, 3, (2, 3)), ("h", 7, 7, (1, 2)),
+                                          ("p", 1, 2, (3, 2)), ("p", 3, 7, (2, 3)), ("p", 6, 7, (2, 2)), ("p", 2, 4, (3, 3))])
+def test_emulated_2d_transfers(kind, pc, pf, n, emu, oracle):
+    nf = tuple(2 * c for c in n) if kind == "h" else n
+    mc, mf = oracle.MatrixFree(2, pc, n), oracle.MatrixFree(2, pf, nf)
+    t = oracle.Transfer(mc, mf, kind)
+    xc, rf = splitmix_src(mc.n_dofs, mc.constrained(), salt=44), splitmix_src(mf.n_dofs, salt=45)
+    d0, c0 = splitmix_src(mf.n_dofs, salt=46), splitmix_src(mc.n_dofs, salt=47)  # "_and_add": the targets are not zero
+    ref_p, ref_r = t.prolongate_and_add(d0.copy(), xc), t.restrict_and_add(c0.copy(), rf)
+    dp, dr = d0.copy(), c0.copy()
+    k = 0 if kind == "h" else 1
+    assert emu.emu2_prolongate_and_add(k, pc, pf, n[0], n[1], C.c_uint(0xF), P(dp), P(xc)) == 0
+    assert emu.emu2_restrict_and_add(k, pc, pf, n[0], n[1], C.c_uint(0xF), P(dr), P(rf)) == 0
+    assert rel_l2(dp, ref_p) < 1e-13 and rel_l2(dr, ref_r) < 1e-13
