@@ -87,6 +87,19 @@ int pmgk_outer3(double *out, const double *lx, const double *ly, const double *l
 /* x_i = ((first_global + i) mod 11), Chebyshev eigenvalue-estimate start vector */
 int pmgk_set_mod11(double *x, int64_t first_global, int64_t n, void *stream);
 
+/* The coarse part of the V-cycle -- levels[0 .. n_levels) coarse -> fine, one degree, geometric transfers, each wholly on this
+   GPU -- as one single-CTA kernel (csrc/pmg_coarse_cycle.h): v_cycle(levels[n_levels-1]) from a zero guess, sol <- cycle(rhs),
+   with the operations of VCycleMultigrid::v_cycle / smooth (include/multigrid/portable_v_cycle_multigrid.h:96-190).
+   P1d_host: HOST (p+1) x (2p+1) h-prolongation matrix. */
+typedef struct pmgk_coarse_level {
+  const pmgk_level *lv;
+  int cheb_degree;       /* smoother degree and parameters of the level */
+  double theta, delta;
+  double *sol, *rhs, *tmp, *res; /* device vectors of the level */
+} pmgk_coarse_level;
+int pmgk_coarse_cycle_supported(const pmgk_level *lv);
+int pmgk_coarse_cycle(const pmgk_coarse_level *levels, int n_levels, int pre, int post, const double *P1d_host, void *stream);
+
 /* transfers (K4-K7).  kind 0 = geometric (fine mesh = coarse refined once, same degree),
    kind 1 = polynomial (same mesh, degree pc < pf).  P1d: device, (pc+1) x nf1 row-major,
    nf1 = 2p+1 (h) or pf+1 (p).  scratch: device doubles, >= pmgk_restrict_scratch_doubles(). */

@@ -25,6 +25,7 @@ struct pmg_vcycle {
   pmg_transfer *tr[PMG_MAX_LEVELS];
   pmg_chebyshev *sm[PMG_MAX_LEVELS];
   pmg_vector *sol[PMG_MAX_LEVELS], *rhs[PMG_MAX_LEVELS], *tmp[PMG_MAX_LEVELS], *res[PMG_MAX_LEVELS];
+  int coarse_top;   /* levels 0 .. coarse_top run as one single-CTA kernel (csrc/pmg_coarse_cycle.h); -1 = none, -2 = undecided */
   int graph_enabled, calls;
   cudaGraphExec_t graph_exec;
   const double *graph_dst, *graph_src;
@@ -61,6 +62,7 @@ int pmg_vcycle_create(pmg_operator *const *ops, pmg_transfer *const *transfers, 
   if (!v) return PMG_ERR_NOMEM;
   v->ctx = ops[0]->ctx; v->n_levels = n_levels; v->pre = pre; v->post = post;
   v->graph_enabled = 1;
+  v->coarse_top = -2;
   for (int l = 0; l < n_levels; ++l) {
     if (!ops[l] || !smoothers[l] || smoothers[l]->op != ops[l] || (l > 0 && !transfers[l])) {
       pmg_set_error("vcycle_create: level %d is incomplete or its smoother belongs to another operator", l);
@@ -109,10 +111,52 @@ int pmg_vcycle_set_graph(pmg_vcycle *v, int enable)
   return PMG_OK;
 }
 
+/* Which levels run inside the single-CTA coarse kernel: the longest prefix 0 .. L of levels of one degree, connected by
+   geometric transfers, each wholly on this GPU and small enough that one CTA's gather loops beat ~23 latency-bound launches
+   per level (work = DoFs x row length <= 3 M multiply-adds per apply: Q1 up to 33^3 DoFs, Q2 up to 17^3).
+   PMG_COARSE_KERNEL=0 keeps every level on the per-level kernels. */
+#define PMG_COARSE_MAX_WORK 3.0e6
+static void choose_coarse_top(pmg_vcycle *v)
+{
+  v->coarse_top = -1;
+  const char *e = getenv("PMG_COARSE_KERNEL");
+  if (e && atoi(e) == 0) return;
+  for (int l = 0; l < v->n_levels && l < 8; ++l) {
+    const pmg_operator *op = v->op[l];
+    if (!pmgk_coarse_cycle_supported(&op->lv) && op->lay.active) break;
+    if (op->ctx->n_ranks > 1 && !op->lay.gathered) break;
+    if (op->degree != v->op[0]->degree || op->coefficient != 0 || op->dim != 3) break;
+    if (l > 0 && v->tr[l]->kind != 0) break;
+    const double n1 = op->degree + 1;
+    if ((double)op->lay.n_global * 8.0 * n1 * n1 * n1 > PMG_COARSE_MAX_WORK) break;
+    v->coarse_top = l;
+  }
+}
+
+static int coarse_cycle(pmg_vcycle *v, int top, pmg_vector *u, const pmg_vector *rhs)
+{
+  if (!v->op[top]->lay.active) return PMG_OK; /* gathered levels live on rank 0 */
+  pmgk_coarse_level cl[8];
+  for (int l = 0; l <= top; ++l) {
+    cl[l].lv = &v->op[l]->lv;
+    cl[l].cheb_degree = v->sm[l]->degree; cl[l].theta = v->sm[l]->theta; cl[l].delta = v->sm[l]->delta;
+    cl[l].sol = (l == top) ? u->d : v->sol[l]->d;
+    cl[l].rhs = (l == top) ? rhs->d : v->rhs[l]->d;
+    cl[l].tmp = v->tmp[l]->d; cl[l].res = v->res[l]->d;
+  }
+  double P[(PMG_MAX_DEGREE + 1) * (2 * PMG_MAX_DEGREE + 1)];
+  pmg_fe_prolongation_h(v->op[0]->degree, P);
+  return pmgk_coarse_cycle(cl, top + 1, v->pre, v->post, P, v->ctx->stream);
+}
+
 /* v_cycle (:128-190).  u holds the iterate on entry unless zero_guess; on return u holds the result. */
 static int v_cycle(pmg_vcycle *v, int level, pmg_vector *u, const pmg_vector *rhs, int zero_guess)
 {
   pmg_vector *cur = u, *other = v->tmp[level], *r = NULL;
+  if (level == v->coarse_top && zero_guess) {
+    PMG_CHECK(mark(v, level, CAT_SMOOTH));
+    return coarse_cycle(v, level, u, rhs);
+  }
   if (level == 0) {
     /* coarsest level: one smooth() (:148-154) */
     PMG_CHECK(mark(v, level, CAT_SMOOTH));
@@ -156,6 +200,7 @@ static int ensure_initialized(pmg_vcycle *v)
 {
   for (int l = 0; l < v->n_levels; ++l)
     if (!v->sm[l]->initialized) PMG_CHECK(pmg_chebyshev_estimate(v->sm[l]));
+  if (v->coarse_top == -2) choose_coarse_top(v);
   return PMG_OK;
 }
 

@@ -267,6 +267,30 @@ def test_vcycle_graph_vs_eager_bitwise(pmg, ctx):
     assert prof.shape == (len(levels), 4) and prof.sum() > 0
 
 
+@pytest.mark.parametrize("kind,p,n", [("h", 1, 32), ("h", 2, 16), ("hp", 4, 8)])
+def test_coarse_cycle_kernel_matches_per_level_kernels(kind, p, n, pmg, ctx, monkeypatch):
+    """The small levels run inside one single-CTA kernel (csrc/pmg_coarse_cycle.h); PMG_COARSE_KERNEL=0 keeps them on the
+    per-level kernels: the two cycles agree to round-off (the gather order inside a row differs)."""
+    levels = hierarchy_levels(kind, p, n)
+    r = None
+    results = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PMG_COARSE_KERNEL", flag)  # read at the cycle's first vmult
+        ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)
+        top = ops[-1]
+        if r is None:
+            r = splitmix_src(top.m(), salt=17)
+        dr, dz = top.vector_from(r), top.initialize_dof_vector()
+        launches = []
+        for rep in range(3):
+            before = ctx.launch_count()
+            mg.vmult(dz, dr)
+            launches.append(ctx.launch_count() - before)
+        results.append((dz.export_host(), launches[0]))
+    assert rel_l2(results[1][0], results[0][0]) <= 1e-12
+    assert results[1][1] < results[0][1]  # fewer launches: the coarse levels are one kernel
+
+
 def test_host_buffer_entry_points(pmg, ctx, oracle):
     p, n = 2, (6, 6, 6)
     mf = oracle.MatrixFree(3, p, n)

@@ -12,7 +12,7 @@ import re
 import numpy as np
 import pytest
 
-from helpers import rel_l2, splitmix_src
+from helpers import hierarchy_levels, rel_l2, splitmix_src
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 dp = C.POINTER(C.c_double)
@@ -314,3 +314,22 @@ def test_emulated_2d_transfers(kind, pc, pf, n, emu, oracle):
     assert emu.emu2_prolongate_and_add(k, pc, pf, n[0], n[1], C.c_uint(0xF), P(dp), P(xc)) == 0
     assert emu.emu2_restrict_and_add(k, pc, pf, n[0], n[1], C.c_uint(0xF), P(dr), P(rf)) == 0
     assert rel_l2(dp, ref_p) < 1e-13 and rel_l2(dr, ref_r) < 1e-13
+
+
+# ---- the single-CTA coarse V-cycle program (csrc/pmg_coarse_cycle.h) under the host emulator ------------------------
+@pytest.mark.parametrize("p,n,faces", [(1, 8, 0x3F), (2, 4, 0x3F), (1, 4, 0x15), (3, 2, 0x3F), (4, 2, 0x3F)])
+def test_emulated_coarse_cycle_matches_oracle_vcycle(p, n, faces, emu, oracle):
+    """All levels of a small h-hierarchy in one program: same result as the oracle's VCycleMultigrid::vmult (the Chebyshev
+    parameters come from the oracle's eigenvalue estimates, as the host passes its own to the kernel)."""
+    levels = hierarchy_levels("h", p, n)
+    mfs = [oracle.MatrixFree(3, q, m, faces=faces) for (q, m) in levels]
+    trs = [oracle.Transfer(mfs[l - 1], mfs[l], "h") for l in range(1, len(levels))]
+    vc = oracle.VCycle(mfs, trs)
+    est = vc.estimate()
+    L = len(levels)
+    deg = (C.c_int * L)(*[e[2] for e in est])
+    theta, delta = (C.c_double * L)(*[e[4] for e in est]), (C.c_double * L)(*[e[5] for e in est])
+    r = splitmix_src(mfs[-1].n_dofs, mfs[-1].constrained(), salt=61)
+    out = np.full(mfs[-1].n_dofs, np.nan)
+    assert emu.emu_coarse_cycle(p, L, (C.c_int * 3)(1, 1, 1), C.c_uint(faces), 2, 2, deg, theta, delta, P(out), P(r)) == 0
+    assert rel_l2(out, vc.vmult(r)) < 1e-12
