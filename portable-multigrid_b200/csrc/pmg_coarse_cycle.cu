@@ -12,10 +12,11 @@ struct DeviceExec {
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
+template <int P>
 __global__ void __launch_bounds__(kThreads, 1) k_coarse_cycle(const __grid_constant__ PmgCoarseParams q)
 {
   DeviceExec ex;
-  PmgCoarseCycle<kThreads>::run(q, ex);
+  PmgCoarseCycle<kThreads, P>::run(q, ex);
 }
 
 } // namespace
@@ -48,7 +49,13 @@ extern "C" int pmgk_coarse_cycle(const pmgk_coarse_level *levels, int n_levels, 
     c.sol = levels[l].sol; c.rhs = levels[l].rhs; c.tmp = levels[l].tmp; c.res = levels[l].res;
     if (!c.sol || !c.rhs || !c.tmp || !c.res || !c.dinv_tab) return PMG_ERR_ARG;
   }
-  k_coarse_cycle<<<1, kThreads, 0, (cudaStream_t)stream>>>(q);
+  switch (p) {
+    case 1: k_coarse_cycle<1><<<1, kThreads, 0, (cudaStream_t)stream>>>(q); break;
+    case 2: k_coarse_cycle<2><<<1, kThreads, 0, (cudaStream_t)stream>>>(q); break;
+    case 3: k_coarse_cycle<3><<<1, kThreads, 0, (cudaStream_t)stream>>>(q); break;
+    case 4: k_coarse_cycle<4><<<1, kThreads, 0, (cudaStream_t)stream>>>(q); break;
+    default: return PMG_ERR_UNSUPPORTED;
+  }
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;

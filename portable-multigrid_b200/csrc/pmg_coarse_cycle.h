@@ -13,6 +13,10 @@
 //   A u (row gx, gy, gz) = sum over the <= 8 cells containing the DoF of the tensor-product cell matrix row
 //       cx K (x) M (x) M + cy M (x) K (x) M + cz M (x) M (x) K,  Dirichlet values read as 0, Dirichlet rows = identity;
 //   prolongation: a fine DoF takes its value from one coarse cell that contains it; restriction: transposed gather.
+// STATUS: opt-in (PMG_COARSE_KERNEL=1).  Measured on B200 it is slower than the per-level kernels inside the CUDA graph at every
+// size bound (profiles/r01_coarse_cycle_kernel_sweep.txt): a block barrier plus an L2 round trip per operation and one SM's
+// worth of gather throughput cost more than the 5.4 us a per-level launch costs.  Kept, tested, as the starting point for a
+// shared-memory / thread-block-cluster version.
 // Written against the executor interface of the other tile programs (for_each_thread / sync): the same source is the
 // CUDA kernel (csrc/pmg_coarse_cycle.cu) and runs under the host emulator (tests/emu/emu_coarse.cpp).
 #pragma once
@@ -46,7 +50,8 @@ struct PmgCoarseParams {
   PmgCoarseLevel lv[PMG_CC_MAX_LEVELS];
 };
 
-template <int NT>
+// NT: threads of the CTA; P: the levels' degree (compile time: the gather loops unroll)
+template <int NT, int P>
 struct PmgCoarseCycle {
   static PMG_HD bool dirichlet(const PmgCoarseParams &q, const PmgCoarseLevel &l, int gx, int gy, int gz)
   {
@@ -59,7 +64,7 @@ struct PmgCoarseCycle {
   // (A u)(gx, gy, gz) without the Dirichlet identity
   static PMG_HD double row(const PmgCoarseParams &q, const PmgCoarseLevel &l, const double *u, int gx, int gy, int gz)
   {
-    const int p = q.p, n1 = p + 1;
+    constexpr int p = P, n1 = p + 1;
     const unsigned f = q.faces;
     double acc = 0.0;
     for (int ez = 0; ez < 2; ++ez) {
@@ -71,10 +76,12 @@ struct PmgCoarseCycle {
         for (int ex = 0; ex < 2; ++ex) {
           const int cx = gx / p - ex, i = gx - cx * p;
           if (cx < 0 || cx >= l.nx || i > p) continue;
+#pragma unroll
           for (int kk = 0; kk < n1; ++kk) {
             const int z = cz * p + kk;
             if ((z == 0 && (f >> 4 & 1u)) || (z == l.Nz - 1 && (f >> 5 & 1u))) continue;
             const double mz = q.M[k * n1 + kk], kz = q.K[k * n1 + kk];
+#pragma unroll
             for (int jj = 0; jj < n1; ++jj) {
               const int y = cy * p + jj;
               if ((y == 0 && (f >> 2 & 1u)) || (y == l.Ny - 1 && (f >> 3 & 1u))) continue;
@@ -82,6 +89,7 @@ struct PmgCoarseCycle {
               const double a = l.cx * my * mz, b = l.cy * ky * mz + l.cz * my * kz;
               const double *r = u + ((int64_t)z * l.Ny + y) * l.Nx + cx * p;
               double s = 0.0;
+#pragma unroll
               for (int ii = 0; ii < n1; ++ii) {
                 const int x = cx * p + ii;
                 if ((x == 0 && (f & 1u)) || (x == l.Nx - 1 && (f >> 1 & 1u))) continue;
@@ -100,7 +108,7 @@ struct PmgCoarseCycle {
   static PMG_HD void apply(const PmgCoarseParams &q, const PmgCoarseLevel &l, int tid, int mode, const double *u, const double *b,
                            const double *xold, double *out, double f1, double f2)
   {
-    const int T = q.p + 2;
+    constexpr int T = P + 2;
     const int64_t n = (int64_t)l.Nx * l.Ny * l.Nz;
     for (int64_t g = tid; g < n; g += NT) {
       const int gx = (int)(g % l.Nx), gy = (int)((g / l.Nx) % l.Ny), gz = (int)(g / ((int64_t)l.Nx * l.Ny));
@@ -111,7 +119,7 @@ struct PmgCoarseCycle {
       double v;
       if (mode == 1) v = r;
       else {
-        const double dinv = dir ? 1.0 : l.dinv_tab[pos_type(gx, l.Nx, q.p) + T * (pos_type(gy, l.Ny, q.p) + T * pos_type(gz, l.Nz, q.p))];
+        const double dinv = dir ? 1.0 : l.dinv_tab[pos_type(gx, l.Nx, P) + T * (pos_type(gy, l.Ny, P) + T * pos_type(gz, l.Nz, P))];
         const double corr = f2 * dinv * r;
         v = (mode == 2) ? uc + corr : uc + f1 * (uc - (xold ? xold[g] : 0.0)) + corr;
       }
@@ -122,13 +130,13 @@ struct PmgCoarseCycle {
   // out = f Dinv b (first Chebyshev step from a zero guess)
   static PMG_HD void scale_dinv(const PmgCoarseParams &q, const PmgCoarseLevel &l, int tid, double f, const double *b, double *out)
   {
-    const int T = q.p + 2;
+    constexpr int T = P + 2;
     const int64_t n = (int64_t)l.Nx * l.Ny * l.Nz;
     for (int64_t g = tid; g < n; g += NT) {
       const int gx = (int)(g % l.Nx), gy = (int)((g / l.Nx) % l.Ny), gz = (int)(g / ((int64_t)l.Nx * l.Ny));
       const double dinv = dirichlet(q, l, gx, gy, gz)
                               ? 1.0
-                              : l.dinv_tab[pos_type(gx, l.Nx, q.p) + T * (pos_type(gy, l.Ny, q.p) + T * pos_type(gz, l.Nz, q.p))];
+                              : l.dinv_tab[pos_type(gx, l.Nx, P) + T * (pos_type(gy, l.Ny, P) + T * pos_type(gz, l.Nz, P))];
       out[g] = f * dinv * b[g];
     }
   }
@@ -143,7 +151,7 @@ struct PmgCoarseCycle {
   static PMG_HD void restrict_to(const PmgCoarseParams &q, const PmgCoarseLevel &c, const PmgCoarseLevel &f, int tid, double *dst,
                                  const double *src)
   {
-    const int p = q.p, NF = 2 * p + 1, fstep = 2 * p;
+    constexpr int p = P, NF = 2 * p + 1, fstep = 2 * p;
     const int64_t n = (int64_t)c.Nx * c.Ny * c.Nz;
     for (int64_t g = tid; g < n; g += NT) {
       const int X = (int)(g % c.Nx), Y = (int)((g / c.Nx) % c.Ny), Z = (int)(g / ((int64_t)c.Nx * c.Ny));
@@ -187,7 +195,7 @@ struct PmgCoarseCycle {
   static PMG_HD void prolongate(const PmgCoarseParams &q, const PmgCoarseLevel &c, const PmgCoarseLevel &f, int tid, double *dst,
                                 const double *src, bool add)
   {
-    const int p = q.p, NC = p + 1, NF = 2 * p + 1, fstep = 2 * p;
+    constexpr int p = P, NC = p + 1, NF = 2 * p + 1, fstep = 2 * p;
     const int64_t n = (int64_t)f.Nx * f.Ny * f.Nz;
     for (int64_t g = tid; g < n; g += NT) {
       const int xf = (int)(g % f.Nx), yf = (int)((g / f.Nx) % f.Ny), zf = (int)(g / ((int64_t)f.Nx * f.Ny));

@@ -111,16 +111,19 @@ int pmg_vcycle_set_graph(pmg_vcycle *v, int enable)
   return PMG_OK;
 }
 
-/* Which levels run inside the single-CTA coarse kernel: the longest prefix 0 .. L of levels of one degree, connected by
-   geometric transfers, each wholly on this GPU and small enough that one CTA's gather loops beat ~23 latency-bound launches
-   per level (work = DoFs x row length <= 3 M multiply-adds per apply: Q1 up to 33^3 DoFs, Q2 up to 17^3).
-   PMG_COARSE_KERNEL=0 keeps every level on the per-level kernels. */
-#define PMG_COARSE_MAX_WORK 3.0e6
+/* Which levels run inside the single-CTA coarse kernel (csrc/pmg_coarse_cycle.h): the longest prefix 0 .. L of levels of one
+   degree, connected by geometric transfers, each wholly on this GPU, with DoFs x row length <= PMG_COARSE_MAX_WORK
+   multiply-adds per apply.  OFF by default: measured on B200 (tools/coarse_sweep.py, profiles/r01_coarse_cycle_kernel_sweep.txt)
+   the per-level kernels inside the CUDA graph (5.4 us per operation on the small levels) beat the single CTA at every bound
+   -- C2 cycle 6.62 ms without it, 6.81 / 7.04 / 8.75 ms with levels up to 5^3 / 9^3 / 17^3 DoFs inside; one SM's gather loops
+   with a block barrier and an L2 round trip per operation cost 8 us and more.  PMG_COARSE_KERNEL=1 enables it (kept for the
+   next round: vectors in shared memory, a thread-block cluster instead of one CTA). */
+#define PMG_COARSE_MAX_WORK 1.0e5
 static void choose_coarse_top(pmg_vcycle *v)
 {
   v->coarse_top = -1;
   const char *e = getenv("PMG_COARSE_KERNEL");
-  if (e && atoi(e) == 0) return;
+  if (!e || atoi(e) == 0) return;
   for (int l = 0; l < v->n_levels && l < 8; ++l) {
     const pmg_operator *op = v->op[l];
     if (!pmgk_coarse_cycle_supported(&op->lv) && op->lay.active) break;
@@ -128,7 +131,8 @@ static void choose_coarse_top(pmg_vcycle *v)
     if (op->degree != v->op[0]->degree || op->coefficient != 0 || op->dim != 3) break;
     if (l > 0 && v->tr[l]->kind != 0) break;
     const double n1 = op->degree + 1;
-    if ((double)op->lay.n_global * 8.0 * n1 * n1 * n1 > PMG_COARSE_MAX_WORK) break;
+    const char *w = getenv("PMG_COARSE_MAX_WORK");
+    if ((double)op->lay.n_global * 8.0 * n1 * n1 * n1 > (w ? atof(w) : PMG_COARSE_MAX_WORK)) break;
     v->coarse_top = l;
   }
 }

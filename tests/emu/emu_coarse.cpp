@@ -46,6 +46,12 @@ extern "C" int emu_coarse_cycle(int p, int n_levels, const int *n0, unsigned fac
   q.lv[n_levels - 1].sol = dst;
   q.lv[n_levels - 1].rhs = const_cast<double *>(src);
   HostExecC ex;
-  PmgCoarseCycle<1024>::run(q, ex);
+  switch (p) {
+    case 1: PmgCoarseCycle<1024, 1>::run(q, ex); break;
+    case 2: PmgCoarseCycle<1024, 2>::run(q, ex); break;
+    case 3: PmgCoarseCycle<1024, 3>::run(q, ex); break;
+    case 4: PmgCoarseCycle<1024, 4>::run(q, ex); break;
+    default: return -3;
+  }
   return 0;
 }

@@ -269,13 +269,14 @@ def test_vcycle_graph_vs_eager_bitwise(pmg, ctx):
 
 @pytest.mark.parametrize("kind,p,n", [("h", 1, 32), ("h", 2, 16), ("hp", 4, 8)])
 def test_coarse_cycle_kernel_matches_per_level_kernels(kind, p, n, pmg, ctx, monkeypatch):
-    """The small levels run inside one single-CTA kernel (csrc/pmg_coarse_cycle.h); PMG_COARSE_KERNEL=0 keeps them on the
-    per-level kernels: the two cycles agree to round-off (the gather order inside a row differs)."""
+    """PMG_COARSE_KERNEL=1 runs the small levels inside one single-CTA kernel (csrc/pmg_coarse_cycle.h; off by default, it
+    measured slower than the per-level kernels): the two cycles agree to round-off (the gather order inside a row differs)."""
     levels = hierarchy_levels(kind, p, n)
     r = None
     results = []
     for flag in ("0", "1"):
         monkeypatch.setenv("PMG_COARSE_KERNEL", flag)  # read at the cycle's first vmult
+        monkeypatch.setenv("PMG_COARSE_MAX_WORK", "4e5")
         ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)
         top = ops[-1]
         if r is None:
