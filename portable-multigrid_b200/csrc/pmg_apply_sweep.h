@@ -200,7 +200,10 @@ PMG_HD constexpr int pmg_sweep_canon(int i, int j)
 // FM: -1 = the epilogue mode is the launch parameter p.mode; 0..3 = the kernel is compiled for that one mode and drops the
 // other three epilogue variants from its code (measured on B200, gpurun_out/exp17: apply +4 % at Q4, +10 % at Q2 / Q3,
 // +30 % at Q5 where it frees 48 registers; fused step +1..5 %)
-template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1>
+// SG: the y lines of phase 1 and the x lines of phase 2 are cut into SG segments of cells, each marched by its own thread (a
+// segment starts from the partial cell before it, as the tile's first segment starts from the halo cell): SG x the work items
+// in the two phases that fill only half of the CTA, for one partial cell more per line and segment
+template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1>
 struct PmgSweepTile {
   static constexpr int N1 = P + 1;
   static PMG_HD int mode_of(const PmgSweepParams<P> &p) { return FM >= 0 ? FM : p.mode; }
@@ -230,8 +233,11 @@ struct PmgSweepTile {
   static constexpr int LD_RPI = 32 / LD_LPR;  // rows per warp instruction
   static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return (epilogue_inputs ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
   static constexpr int SMEM_DOUBLES = BAR_OFFSET_EPI + NBAR;
-  static constexpr int NITEM1 = XW * NPS;
-  static constexpr int IT2 = (RW * NPS + NT - 1) / NT; // phase-2 items per thread
+  static constexpr int BXS = (BX + SG - 1) / SG, BYS = (BY + SG - 1) / SG; // cells per segment
+  static constexpr int NITEM1 = XW * NPS * SG;
+  static constexpr int IT2 = (RW * NPS * SG + NT - 1) / NT; // phase-2 items per thread
+  static constexpr int NT2 = ((RW * NPS * SG + 31) / 32 * 32 < NT) ? (RW * NPS * SG + 31) / 32 * 32 : NT; // threads that can hold a phase-2 item in round 0
+  static_assert(SG >= 1 && SG <= 2 && SG <= BX && SG <= BY, "one or two segments per line (seed2 holds one hand-over)");
   static constexpr int NCOL = (CW * RW + NT - 1) / NT; // dof columns per thread in phase 3
   static_assert(NT % 32 == 0, "whole warps: the last one is the cp.async loader");
   static_assert(CW <= 255 && RW <= 255, "column coordinates are packed into 8 bits each (ThreadState::info)");
@@ -250,7 +256,8 @@ struct PmgSweepTile {
     double uP[NCOL];    // u of that plane (epilogue input of the next layer's plane 0)
     double dinv[NCOL][P]; // inverse diagonal of the column's planes k = 0..P-1 of an interior layer (CHEB modes, table)
     int info[NCOL];     // ox | oy << 8 | Dirichlet-in-xy << 16 | x position type << 20 | y position type << 24; -1 = none
-    int item2[IT2];     // phase-2 item: row | plane << 16; -1 = none
+    int item2[IT2];     // phase-2 item: row | plane << 16 | segment << 24; -1 = none
+    double seed2[SG > 1 ? IT2 : 1][4]; // SG > 1: what a phase-2 item reads before the in-place sweep starts (phase2_seed)
   };
 
   struct TileGeom {
@@ -313,8 +320,9 @@ struct PmgSweepTile {
 #pragma unroll
     for (int i = 0; i < IT2; ++i) { // rows fastest: the lanes of a warp walk down a column of the buffer
       const int item = tid + i * NT;
-      const int k = item / t.rows;
-      st.item2[i] = (k < NPS) ? ((item - k * t.rows) | (k << 16)) : -1;
+      const int kk = item / t.rows;
+      const int seg = kk / NPS, k = kk - seg * NPS;
+      st.item2[i] = (seg < SG) ? ((item - kk * t.rows) | (k << 16) | (seg << 24)) : -1;
     }
   }
 
@@ -419,17 +427,23 @@ struct PmgSweepTile {
   {
     const bool dir_lo = (p.faces >> 2 & 1u), dir_hi = (p.faces >> 3 & 1u);
     for (int item = tid; item < NITEM1; item += NT) {
-      const int xl = item % XW, k = item / XW;
+      const int seg = (SG == 1) ? 0 : item / (XW * NPS);
+      const int rem = item - seg * (XW * NPS);
+      const int xl = rem % XW, k = rem / XW;
       if (k >= npl) continue;
       const int gx = (t.cx0 - 1) * P + xl;
       if (gx < 0 || gx >= p.Nx) continue;
+      const int c_lo = seg * BYS;             // first cell of the segment
+      if (c_lo >= t.ncy) continue;
+      const bool last_seg = (c_lo + BYS >= t.ncy); // the segment holds the tile's last valid cell
       const int gz = gz0 + k;
       double *Cc = Cb + k * CPLANE + xl;       // row r: Cc[r * XP]
       double *Dc = Db + k * CPLANE + xl;
       const bool zero_line = (gx == 0 && (p.faces & 1u)) || (gx == p.Nx - 1 && (p.faces >> 1 & 1u)) ||
                              (gz == 0 && (p.faces >> 4 & 1u)) || (gz == p.Nz - 1 && (p.faces >> 5 & 1u));
       if (zero_line) { // Dirichlet values read as 0 (:250-254): the whole line of c, d vanishes
-        for (int r = 0; r < t.rows; ++r) { Cc[r * XP] = 0.0; Dc[r * XP] = 0.0; }
+        const int r_hi = last_seg ? t.rows : (c_lo + BYS) * P;
+        for (int r = c_lo * P; r < r_hi; ++r) { Cc[r * XP] = 0.0; Dc[r * XP] = 0.0; }
         continue;
       }
       // row yl of the column is at Ae[yl * XPA] for even yl and Ao[yl * XPA] for odd yl (the row shift alternates
@@ -439,11 +453,11 @@ struct PmgSweepTile {
       const double *Ao = A + k * APLANE + xl + (s0 ^ t.nxodd);
 #define PMG_AROW(yl) ((((yl) & 1) ? Ao : Ae)[(yl) * XPA])
       double cc = 0.0, cd = 0.0, v0;
-      if (t.cy0 > 0) { // partial cell below the tile: only its contribution to the first owned row
+      if (t.cy0 + c_lo > 0) { // partial cell below the segment (the halo cell for the first one): only its contribution to the segment's first row
         double v[N1];
 #pragma unroll
-        for (int j = 0; j < N1; ++j) v[j] = PMG_AROW(j);
-        if (t.cy0 == 1 && dir_lo) v[0] = 0.0;
+        for (int j = 0; j < N1; ++j) v[j] = PMG_AROW(c_lo * P + j);
+        if (t.cy0 + c_lo == 1 && dir_lo) v[0] = 0.0;
 #pragma unroll
         for (int j = 0; j < N1; ++j) { cc = fma(PMG_M(P, j), v[j], cc); cd = fma(PMG_KY(P, j), v[j], cd); }
         v0 = v[P];
@@ -451,7 +465,8 @@ struct PmgSweepTile {
         v0 = dir_lo ? 0.0 : PMG_AROW(P);
       }
 #pragma unroll
-      for (int c = 0; c < BY; ++c) {
+      for (int ci = 0; ci < BYS; ++ci) {
+        const int c = c_lo + ci;
         if (c < t.ncy) {
           double vj = v0;
           double sc[N1], sd[N1];
@@ -473,24 +488,62 @@ struct PmgSweepTile {
           cc = sc[P]; cd = sd[P]; v0 = vj;
         }
       }
-      if (t.y_end) { Cc[t.ncy * P * XP] = cc; Dc[t.ncy * P * XP] = cd; }
+      if (t.y_end && last_seg) { Cc[t.ncy * P * XP] = cc; Dc[t.ncy * P * XP] = cd; }
 #undef PMG_AROW
     }
   }
 
-  // ---- phase 2: x sweep in place.  item = (row r, plane k): (c, d) -> (g, m) ---------------------------------
+  // ---- phase 2: x sweep in place.  item = (row r, plane k, segment): (c, d) -> (g, m) ----------------------------
+  // SG > 1: the segments of a row run concurrently and in place, so whatever a segment needs of values another segment
+  // overwrites is read first (phase2_seed; the phase-2 threads then meet at a barrier of their own): a later segment's start --
+  // the partial sums of the cell before it and the (c, d) of the vertex it starts at -- and an earlier segment's last input, the
+  // (c, d) of the vertex where the next segment starts.  seed2 = {cg, cm, c0, d0} resp. {c_end, d_end, -, -}.
+  static PMG_HD void phase2_seed(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *Cb, const double *Db, int npl)
+  {
+    if (SG == 1) return;
+#pragma unroll
+    for (int it = 0; it < IT2; ++it) {
+      const int item = st.item2[it];
+      if (item < 0) continue;
+      const int r = item & 0xFFFF, k = (item >> 16) & 0xFF, seg = item >> 24;
+      if (k >= npl) continue;
+      const double *Cr = Cb + k * CPLANE + r * XP;
+      const double *Dr = Db + k * CPLANE + r * XP;
+      const int i_lo = seg * BXS;
+      if (i_lo >= t.ncx) continue;
+      if (seg > 0) {
+        double cg = 0.0, cm = 0.0, c[N1], d[N1];
+#pragma unroll
+        for (int j = 0; j < N1; ++j) { c[j] = Cr[i_lo * P + j]; d[j] = Dr[i_lo * P + j]; }
+#pragma unroll
+        for (int j = 0; j < N1; ++j) {
+          cg = fma(PMG_KX(P, j), c[j], fma(PMG_M(P, j), d[j], cg));
+          cm = fma(PMG_M(P, j), c[j], cm);
+        }
+        st.seed2[it][0] = cg; st.seed2[it][1] = cm; st.seed2[it][2] = c[P]; st.seed2[it][3] = d[P];
+      } else if (i_lo + BXS < t.ncx) { // first segment with a successor: its last input is the successor's first output
+        st.seed2[it][0] = Cr[P + (i_lo + BXS) * P]; st.seed2[it][1] = Dr[P + (i_lo + BXS) * P];
+      }
+    }
+  }
+
   static PMG_HD void phase2(const PmgSweepParams<P> &p, const TileGeom &t, const ThreadState &st, double *Cb, double *Db, int npl)
   {
 #pragma unroll
     for (int it = 0; it < IT2; ++it) {
       const int item = st.item2[it];
       if (item < 0) continue;
-      const int r = item & 0xFFFF, k = item >> 16;
+      const int r = item & 0xFFFF, k = (item >> 16) & 0xFF, seg = (SG == 1) ? 0 : item >> 24;
       if (k >= npl) continue;
+      const int i_lo = seg * BXS;
+      if (i_lo >= t.ncx) continue;
+      const bool last_seg = (i_lo + BXS >= t.ncx);
       double *Cr = Cb + k * CPLANE + r * XP;
       double *Dr = Db + k * CPLANE + r * XP;
       double cg = 0.0, cm = 0.0, c0, d0;
-      if (t.cx0 > 0) { // partial cell left of the tile: only its contribution to the first owned column
+      if (SG > 1 && seg > 0) {
+        cg = st.seed2[it][0]; cm = st.seed2[it][1]; c0 = st.seed2[it][2]; d0 = st.seed2[it][3];
+      } else if (t.cx0 > 0) { // partial cell left of the tile: only its contribution to the first owned column
         double c[N1], d[N1];
 #pragma unroll
         for (int j = 0; j < N1; ++j) { c[j] = Cr[j]; d[j] = Dr[j]; }
@@ -504,7 +557,8 @@ struct PmgSweepTile {
         c0 = Cr[P]; d0 = Dr[P];
       }
 #pragma unroll
-      for (int i = 0; i < BX; ++i) {
+      for (int ii = 0; ii < BXS; ++ii) {
+        const int i = i_lo + ii;
         if (i < t.ncx) {
           double *Cc = Cr + P + i * P, *Dc = Dr + P + i * P;
           double sg[N1], sm[N1];
@@ -515,6 +569,7 @@ struct PmgSweepTile {
 #pragma unroll
           for (int j = 0; j < N1; ++j) {
             if (j > 0) { cj = Cc[j]; dj = Dc[j]; }
+            if (SG > 1 && j == P && ii == BXS - 1 && !last_seg) { cj = st.seed2[it][0]; dj = st.seed2[it][1]; } // overwritten by the next segment
 #pragma unroll
             for (int kk = 0; kk < N1; ++kk) {
               sg[kk] = fma(PMG_KX(kk, j), cj, fma(PMG_M(kk, j), dj, sg[kk]));
@@ -526,7 +581,7 @@ struct PmgSweepTile {
           cg = sg[P]; cm = sm[P]; c0 = cj; d0 = dj;
         }
       }
-      if (t.x_end) { Cr[P + t.ncx * P] = cg; Dr[P + t.ncx * P] = cm; }
+      if (t.x_end && last_seg) { Cr[P + t.ncx * P] = cg; Dr[P + t.ncx * P] = cm; }
     }
   }
 
@@ -729,6 +784,10 @@ struct PmgSweepTile {
     });
     par_u[0] ^= 1;
     ex.sync();
+    if (SG > 1) {
+      ex.for_each_thread([&](int, ThreadState &st) { phase2_seed(p, t, st, Cb, Db, 1); });
+      ex.sync_some(NT2);
+    }
     ex.for_each_thread([&](int, ThreadState &st) { phase2(p, t, st, Cb, Db, 1); });
     ex.sync();
     ex.for_each_thread([&](int, ThreadState &st) { phase3_init(p, t, st, smem, Cb, Db, cz_first * P); });
@@ -752,6 +811,10 @@ struct PmgSweepTile {
       });
       par_u[cur] ^= 1;
       ex.sync();
+      if (SG > 1) { // the phase-2 threads read what another segment of their row overwrites, then meet at their own barrier
+        ex.for_each_thread([&](int, ThreadState &st) { phase2_seed(p, t, st, Cb, Db, nlay * P); });
+        ex.sync_some(NT2);
+      }
       ex.for_each_thread([&](int tid, ThreadState &st) {
         phase2(p, t, st, Cb, Db, nlay * P);
         if (tid >= NT - 32) pmg_sweep_cp_async_wait_all(); // the loader warp's copies (E for phase 3, u rows for the next step)

@@ -12,6 +12,7 @@ struct PmgSweepDeviceExec {
   typename Tile::ThreadState st;
   template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void sync_some(int n) { if ((int)threadIdx.x < n) asm volatile("bar.sync 1, %0;\n" ::"r"(n) : "memory"); }
 };
 
 template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>

@@ -10,17 +10,25 @@
 template <class Tile>
 struct SweepHostExec {
   std::vector<typename Tile::ThreadState> st;
-  template <class F> void for_each_thread(F f) { for (int t = 0; t < Tile::NT; ++t) f(t, st[t]); }
+  bool reverse = false; // run the threads of a phase in descending order: exposes in-place hazards between threads of one phase
+  template <class F> void for_each_thread(F f)
+  {
+    if (reverse) for (int t = Tile::NT - 1; t >= 0; --t) f(t, st[t]);
+    else for (int t = 0; t < Tile::NT; ++t) f(t, st[t]);
+  }
   void sync() {}
+  void sync_some(int) {}
 };
 
-template <int P, int BX, int BY, int LZ, int NT, int US = 1>
+static bool g_reverse = false;
+
+template <int P, int BX, int BY, int LZ, int NT, int US = 1, int SG = 1>
 static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
                      int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -55,6 +63,7 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
       for (int tx = 0; tx < p.tiles_x; ++tx) {
         SweepHostExec<Tile> ex;
         ex.st.resize(Tile::NT);
+        ex.reverse = g_reverse;
         for (auto &v : smem) v = 1e300; // poison shared memory so stale reads show up
         Tile::run(p, ex, smem.data(), tx, ty, chunk);
       }
@@ -64,13 +73,28 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
 #define ARGS nx, ny, nz, faces, z0, nzl, cz_lo, cz_hi, z_own_lo, z_own_hi, n_chunks, M, K, h, mode, u, b, xold, out, f1, f2, dinv_vec, dinv_tab
 
 // small_tiles != 0 selects deliberately tiny tiles / thread counts so that small meshes exercise many tiles,
-// several items per thread and several columns per thread; 0 = the tiles pmg_apply.cu launches
+// several items per thread and several columns per thread; 0 = the tiles pmg_apply.cu launches;
+// 2, 3 = small tiles with two segments per line (SG = 2), 3 with the threads of every phase run in descending order
 extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, unsigned faces, int z0, int nzl,
                          int cz_lo, int cz_hi, int z_own_lo, int z_own_hi, int n_chunks, const double *M,
                          const double *K, const double *h, int mode, const double *u, const double *b,
                          const double *xold, double *out, double f1, double f2, const double *dinv_vec,
                          const double *dinv_tab)
 {
+  g_reverse = (small_tiles == 3);
+  if (small_tiles >= 2) {
+    switch (degree) {
+      case 1: sweep_go<1, 4, 3, 3, 32, 1, 2>(ARGS); return 0;
+      case 2: sweep_go<2, 3, 4, 2, 32, 0, 2>(ARGS); return 0;
+      case 3: sweep_go<3, 2, 3, 1, 64, 1, 2>(ARGS); return 0;
+      case 4: sweep_go<4, 4, 2, 1, 64, 1, 2>(ARGS); return 0;
+      case 5: sweep_go<5, 2, 2, 1, 32, 0, 2>(ARGS); return 0;
+      case 6: sweep_go<6, 2, 2, 1, 32, 1, 2>(ARGS); return 0;
+      case 7: sweep_go<7, 2, 2, 1, 32, 1, 2>(ARGS); return 0;
+      case 8: sweep_go<8, 2, 2, 1, 64, 0, 2>(ARGS); return 0;
+    }
+    return -3;
+  }
   if (small_tiles) {
     switch (degree) {
       case 1: sweep_go<1, 3, 2, 3, 32>(ARGS); return 0;

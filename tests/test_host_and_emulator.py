@@ -209,6 +209,22 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
     assert rel_l2(got, ref) < 1e-13
 
 
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("small", [2, 3])
+def test_emulated_sweep_with_two_segments_per_line(p, small, emu, oracle):
+    """SG = 2 (csrc/pmg_apply_sweep.h): the y lines of phase 1 and the x lines of phase 2 are marched by two threads each; phase 2
+    works in place, so a segment reads what its neighbour overwrites before either starts.  small = 3 runs the threads of every
+    phase in descending order, which turns a missed hand-over into a wrong result.  (Measured slower on B200, kept as a knob.)"""
+    n = (5, 4, 3) if p < 5 else (4, 3, 2)
+    for faces in (0x3F, 0x15):
+        mf = oracle.MatrixFree(3, p, n, faces=faces)
+        u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (71, 72, 73))
+        Au, dinv = mf.vmult(u), mf.compute_diagonal()
+        assert rel_l2(emu_apply(emu, p, n, u, small=small, chunks=2, faces=faces), Au) < 1e-13
+        ref = u + 0.3 * (u - xo) + 0.7 * dinv * (b - Au)
+        assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.7, small=small, faces=faces), ref) < 1e-13
+
+
 # ---- variable-coefficient tile program (csrc/pmg_apply_var.h) under the host emulator ---------------------
 def emu_var(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, chunks=1, faces=0x3F, slab=None, dinv_vec=None,
             want_dinv=False):

@@ -15,7 +15,10 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #ifndef C_FM
 #define C_FM -1
 #endif
-#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM
+#ifndef C_SG
+#define C_SG 1
+#endif
+#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM, C_SG
 #define STR2(x) #x
 #define STR(x) STR2(x)
 #define CFGSTR STR(C_P) "," STR(C_BX) "," STR(C_BY) "," STR(C_LZ) "," STR(C_NT)
@@ -39,6 +42,7 @@ struct Ex {
   template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
 #endif
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void sync_some(int n) { if ((int)threadIdx.x < n) asm volatile("bar.sync 1, %0;\n" ::"r"(n) : "memory"); }
 };
 __global__ void __launch_bounds__(Tile::NT, MINB) kern(const __grid_constant__ PmgSweepParams<PP> p)
 {
