@@ -500,9 +500,8 @@ struct PmgSweepTile {
   // (c, d) of the vertex where the next segment starts.  seed2 = {cg, cm, c0, d0} resp. {c_end, d_end, -, -}.
   static PMG_HD void phase2_seed(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *Cb, const double *Db, int npl)
   {
-    if (SG == 1) return;
 #pragma unroll
-    for (int it = 0; it < IT2; ++it) {
+    for (int it = 0; it < (SG > 1 ? IT2 : 0); ++it) {
       const int item = st.item2[it];
       if (item < 0) continue;
       const int r = item & 0xFFFF, k = (item >> 16) & 0xFF, seg = item >> 24;
