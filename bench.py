@@ -130,7 +130,7 @@ def measured_peaks():
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v4_cheb_step_q4_c2.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_v5_cheb_step_q4_c2.json")) as f:
             return json.load(f).get("dram_bytes_per_launch")
     except Exception:
         return None
