@@ -65,16 +65,26 @@ def h_levels(p, cells):
     return levels[::-1]
 
 
-# BASELINE.json configs: "c2" = configs[1] (the one the metric is quoted on, default), "c1" = configs[0]
+# BASELINE.json configs: "c2" = configs[1] (the one the metric is quoted on, default), "c1" = configs[0]; "c4" = configs[3]
+# at its per-GPU size (Q3, 160^3 cells = 111 M DoFs per GPU, geometric hierarchy 5 .. 160 cells), "c5" = configs[4] at a
+# single-GPU size (variable coefficient, Q5, 64^3 cells = 33 M DoFs per GPU; the named 160^3 cells need the 8-GPU box),
+# p = 5 -> 2 -> 1 + geometric levels, CG to 1e-10
 CONFIGS = {"c2": {"degree": 4, "cells": 64, "hierarchy": "hp", "cheb_degree": 5},
-           "c1": {"degree": 2, "cells": 64, "hierarchy": "h", "cheb_degree": 3}}
+           "c1": {"degree": 2, "cells": 64, "hierarchy": "h", "cheb_degree": 3},
+           "c4": {"degree": 3, "cells": 160, "hierarchy": "h", "cheb_degree": 5},
+           "c5": {"degree": 5, "cells": 64, "hierarchy": "hp", "cheb_degree": 5, "coefficient": 1, "cg_tol": 1e-10}}
 
 
-def workload_name(p, cells, world, hierarchy="hp", cheb_degree=5):
+def workload_name(p, cells, world, hierarchy="hp", cheb_degree=5, coefficient=0):
     nd = 1
     for c in cells:
         nd *= c * p + 1
-    hier = "hp-multigrid p=4->2->1 + geometric levels" if hierarchy == "hp" else "geometric multigrid, Q%d on every level" % p
+    degs = [p]
+    while degs[-1] > 1:
+        degs.append(max(1, degs[-1] // 2))
+    hier = ("hp-multigrid p=%s + geometric levels" % "->".join(str(d) for d in degs)) if hierarchy == "hp" else "geometric multigrid, Q%d on every level" % p
+    if coefficient:
+        hier = "variable coefficient a = 1/(0.05 + 2|x|^2), " + hier
     return ("3D Poisson Q%d, %dx%dx%d cells (%d DoFs), %s, V(2,2) Chebyshev(%d)-Jacobi, one V-cycle per step"
             % (p, cells[0], cells[1], cells[2], nd, hier, cheb_degree)), nd
 
@@ -254,8 +264,9 @@ def main():
     p = cfg["degree"]
     cells = scaled_cells(cfg["cells"], world)
     levels = hp_levels(p, cells) if cfg["hierarchy"] == "hp" else h_levels(p, cells)
-    name, n_dofs = workload_name(p, cells, world, cfg["hierarchy"], cfg["cheb_degree"])
-    ops, transfers, smoothers, mg = G.build_hierarchy(ctx, levels, degree=cfg["cheb_degree"])
+    coefficient = cfg.get("coefficient", 0)
+    name, n_dofs = workload_name(p, cells, world, cfg["hierarchy"], cfg["cheb_degree"], coefficient)
+    ops, transfers, smoothers, mg = G.build_hierarchy(ctx, levels, degree=cfg["cheb_degree"], coefficient=coefficient)
     top = ops[-1]
     r_host = splitmix_src(n_dofs)
     r, z = top.vector_from(r_host), top.initialize_dof_vector()
@@ -300,11 +311,12 @@ def main():
     # the drivers' solve (program.cc:345-355): CG preconditioned by one V-cycle, to 1e-12 ||b||, on the load vector of f = 1
     rhs, sol = top.initialize_dof_vector(), top.initialize_dof_vector()
     top.assemble_rhs(rhs)
-    G.cg_solve(top, sol, rhs, mg)  # warm-up (also leaves the graph captured)
+    cg_tol = cfg.get("cg_tol", 1e-12)
+    G.cg_solve(top, sol, rhs, mg, rel_tol=cg_tol)  # warm-up (also leaves the graph captured)
     sol.set(0.0)
     barrier()
     t0 = time.perf_counter()
-    cg_it, cg_hist, cg_rc = G.cg_solve(top, sol, rhs, mg)
+    cg_it, cg_hist, cg_rc = G.cg_solve(top, sol, rhs, mg, rel_tol=cg_tol)
     ctx.sync()
     cg_s = max_over_ranks(time.perf_counter() - t0)
     cg = {"iterations": int(cg_it), "converged": cg_rc == 0, "ms": cg_s * 1e3, "gdofs_x_iterations_per_s": n_dofs * max(cg_it, 1) / cg_s / 1e9,
@@ -344,12 +356,15 @@ def main():
 
     peak, peak_src = measured_peaks()
     n_local = n_dofs / world
-    algo_bytes = 32.0 * n_local  # fused Chebyshev step: read u, x_old, b; write x_new (Dinv is a table)
+    # fused Chebyshev step: read u, x_old, b; write x_new (Dinv is a table); variable coefficient: + Dinv vector + one
+    # coefficient per quadrature point
+    bytes_per_dof = 32.0 + ((8.0 + 8.0 * (p + 1) ** 3 / p ** 3) if coefficient else 0.0)
+    algo_bytes = bytes_per_dof * n_local
     achieved = algo_bytes / (ms_step * 1e-3) / 1e9
     n1 = p + 1
     # FP64 work per DoF (kernel K1): the kernel executes 7 one-dimensional sweeps of (p+1)^2 / p FMAs per DoF
     # plus the epilogue; the reference's cell loop needs [24 (p+1)^4 + 39 (p+1)^3] / p^3 flops per DoF
-    flops_per_dof = 2.0 * 7.0 * n1 * n1 / p + 8.0
+    flops_per_dof = (2.0 * 7.0 * n1 * n1 / p + 8.0) if not coefficient else (2.0 * 12.0 * n1 ** 4 / p ** 3 + 8.0)
     ref_flops_per_dof = (24.0 * n1 ** 4 + 39.0 * n1 ** 3) / p ** 3
     fp64 = None
     try:
@@ -375,9 +390,10 @@ def main():
         "cg_solve": cg,
         "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
         "clocks": clocks,
-        "roofline": {"kernel": "pmg_sweep_kernel<%d> (fused Chebyshev step, finest level)" % p, "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "algorithmic_bytes_per_dof": 32, "ms_per_launch": ms_step, "fp64": fp64},
+        "roofline": {"kernel": ("pmg_var_kernel<%d>" if coefficient else "pmg_sweep_kernel<%d>") % p + " (fused Chebyshev step, finest level)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic() if args.config == "c2" and world == 1 else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_dof": bytes_per_dof, "ms_per_launch": ms_step, "fp64": fp64},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
