@@ -49,6 +49,13 @@ enum { PMGK_APPLY = 0, PMGK_RESIDUAL = 1, PMGK_CHEB_FIRST = 2, PMGK_CHEB_STEP = 
    (reference include/operators/portable_laplace_operator.h:557-719) */
 int pmgk_apply(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                double *out, double f1, double f2, void *stream);
+/* The same launch in two parts, for slabs with neighbours: PMGK_PART_INTERIOR = the z-chunks that read no ghost plane,
+   PMGK_PART_BOUNDARY = the first and the last chunk.  INTERIOR + BOUNDARY write exactly what PMGK_PART_ALL writes.
+   pmgk_apply_splits: 1 if the level's launch can be split (line-marching kernel, >= 3 chunks). */
+enum { PMGK_PART_ALL = 0, PMGK_PART_INTERIOR = 1, PMGK_PART_BOUNDARY = 2 };
+int pmgk_apply_part(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                    double *out, double f1, double f2, int part, void *stream);
+int pmgk_apply_splits(const pmgk_level *lv, int mode);
 /* number of kernel launches pmgk_apply issues (1) and the launch geometry it would use */
 int pmgk_apply_geometry(const pmgk_level *lv, int *grid, int *block, int *smem_bytes, int *n_chunks);
 

@@ -87,7 +87,7 @@ static int launch(const pmgk_level *lv, int mode, const double *u, const double 
 // line-marching kernel, one translation unit per epilogue mode: csrc/pmg_apply_sweep_m<mode>.cu
 #define PMG_SWEEP_DECL(m) \
   int pmg_sweep_dispatch_m##m(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, \
-                              double f2, cudaStream_t s, int *geom);
+                              double f2, cudaStream_t s, int *geom, int part);
 PMG_SWEEP_DECL(0) PMG_SWEEP_DECL(1) PMG_SWEEP_DECL(2) PMG_SWEEP_DECL(3)
 #undef PMG_SWEEP_DECL
 
@@ -100,8 +100,12 @@ int pmg_var_dispatch(const pmgk_level *lv, int mode, const double *u, const doub
                      double f1, double f2, cudaStream_t s, int *geom);
 
 static int dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
-                    double *out, double f1, double f2, cudaStream_t s, int *geom)
+                    double *out, double f1, double f2, cudaStream_t s, int *geom, int part = PMGK_PART_ALL)
 {
+  const int64_t n_loc = (int64_t)lv->Nx * lv->Ny * lv->nzl;
+  const bool sweep_kernel = lv->dim == 3 && !lv->coef &&
+                            (lv->tile_variant == 1 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
+  if (part != PMGK_PART_ALL && !sweep_kernel) return PMG_ERR_UNSUPPORTED; /* only the line-marching kernel launches in parts */
   if (lv->dim == 2) return pmg_dim2_apply(lv, mode, u, b, xold, out, f1, f2, s, geom);
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
   if (lv->coef) return pmg_var_dispatch(lv, mode, u, b, xold, out, f1, f2, s, geom);
@@ -114,10 +118,10 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
   const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
   if (lv->tile_variant == 1 || (lv->tile_variant == 0 && !small_level)) {
     switch (mode) { /* one kernel per epilogue mode: csrc/pmg_apply_sweep_m<mode>.cu */
-      case PMGK_APPLY: return pmg_sweep_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom);
-      case PMGK_RESIDUAL: return pmg_sweep_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom);
-      case PMGK_CHEB_FIRST: return pmg_sweep_dispatch_m2(lv, u, b, xold, out, f1, f2, s, geom);
-      case PMGK_CHEB_STEP: return pmg_sweep_dispatch_m3(lv, u, b, xold, out, f1, f2, s, geom);
+      case PMGK_APPLY: return pmg_sweep_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom, part);
+      case PMGK_RESIDUAL: return pmg_sweep_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom, part);
+      case PMGK_CHEB_FIRST: return pmg_sweep_dispatch_m2(lv, u, b, xold, out, f1, f2, s, geom, part);
+      case PMGK_CHEB_STEP: return pmg_sweep_dispatch_m3(lv, u, b, xold, out, f1, f2, s, geom, part);
       default: return PMG_ERR_ARG;
     }
   }
@@ -153,6 +157,22 @@ extern "C" int pmgk_apply(const pmgk_level *lv, int mode, const double *u, const
   if (mode != PMGK_APPLY && !b) return PMG_ERR_ARG;
   if (u == out) return PMG_ERR_ARG; /* the halo of u is read by neighbouring tiles */
   return dispatch(lv, mode, u, b, xold, out, f1, f2, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int pmgk_apply_part(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                               double *out, double f1, double f2, int part, void *stream)
+{
+  if (!lv || !u || !out) return PMG_ERR_ARG;
+  if (mode != PMGK_APPLY && !b) return PMG_ERR_ARG;
+  if (u == out) return PMG_ERR_ARG;
+  return dispatch(lv, mode, u, b, xold, out, f1, f2, (cudaStream_t)stream, nullptr, part);
+}
+
+extern "C" int pmgk_apply_splits(const pmgk_level *lv, int mode)
+{
+  int g[4] = {0, 0, 0, 0};
+  if (!lv) return 0;
+  return dispatch(lv, mode, (const double *)16, (const double *)16, nullptr, (double *)32, 0, 0, 0, g, PMGK_PART_INTERIOR) == 0;
 }
 
 extern "C" int pmgk_apply_geometry(const pmgk_level *lv, int *grid, int *block, int *smem_bytes, int *n_chunks)

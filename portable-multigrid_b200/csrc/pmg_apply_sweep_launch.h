@@ -15,9 +15,11 @@ struct PmgSweepDeviceExec {
   __device__ __forceinline__ void sync_some(int n) { if ((int)threadIdx.x < n) asm volatile("bar.sync 1, %0;\n" ::"r"(n) : "memory"); }
 };
 
+// chunk_first, chunk_stride: the launch's CTAs work on z-chunks chunk_first + i * chunk_stride (all chunks: 0, 1; the two
+// chunks that touch the slab's ghost planes: 0, n_chunks - 1; the others: 1, 1)
 template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>
 __global__ void __launch_bounds__(NT, MINB)
-pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p)
+pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
   using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM>;
   extern __shared__ __align__(128) double pmg_sweep_smem[];
@@ -25,16 +27,17 @@ pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p)
   const int b = blockIdx.x;
   const int tile_x = b % p.tiles_x;
   const int tile_y = (b / p.tiles_x) % p.tiles_y;
-  const int chunk = b / (p.tiles_x * p.tiles_y);
+  const int chunk = chunk_first + (b / (p.tiles_x * p.tiles_y)) * chunk_stride;
   Tile::run(p, ex, pmg_sweep_smem, tile_x, tile_y, chunk);
 }
 
 // number of z-chunks: minimise waves * (layers + recomputed layer and plane below the chunk)
-void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int *n_chunks, int *layers_per_chunk)
+void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int min_chunks, int *n_chunks, int *layers_per_chunk)
 {
   double best_cost = -1;
   int best_c = 1;
-  for (int c = 1; c <= layers; ++c) {
+  if (min_chunks > layers) min_chunks = layers;
+  for (int c = min_chunks; c <= layers; ++c) {
     const int lpc = (layers + c - 1) / c;
     const int used = (layers + lpc - 1) / lpc;
     if (used != c) continue;
@@ -48,7 +51,7 @@ void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int *n_ch
 
 template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>
 int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1,
-                 double f2, cudaStream_t stream, int *geom)
+                 double f2, cudaStream_t stream, int *geom, int part)
 {
   using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM>;
   PmgSweepParams<P> p;
@@ -74,14 +77,23 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
     configured = 1;
   }
   const int slots = pmgk_device_sm_count() * ctas_per_sm;
-  choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, &p.n_chunks, &p.layers_per_chunk);
+  // a slab with neighbours gets at least three chunks, so that the launch can be split into the chunks that read ghost planes
+  // (first and last) and the others, which run while the ghost planes are in flight (host/pmg_operator.c)
+  const bool slab = (lv->cz_lo > 0 || lv->cz_hi < lv->nz);
+  choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, slab ? 3 : 1, &p.n_chunks, &p.layers_per_chunk);
   pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
   p.mode = FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
-  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  int chunk_first = 0, chunk_stride = 1, chunk_count = p.n_chunks;
+  if (part != PMGK_PART_ALL) {
+    if (p.n_chunks < 3) return PMG_ERR_UNSUPPORTED;
+    if (part == PMGK_PART_INTERIOR) { chunk_first = 1; chunk_count = p.n_chunks - 2; }
+    else { chunk_stride = p.n_chunks - 1; chunk_count = 2; }
+  }
+  const int grid = p.tiles_x * p.tiles_y * chunk_count;
   if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
   if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
-  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM><<<grid, NT, smem_bytes, stream>>>(p);
+  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM><<<grid, NT, smem_bytes, stream>>>(p, chunk_first, chunk_stride);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
@@ -93,11 +105,11 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
 #define PMG_SWEEP_CAT(a, b) PMG_SWEEP_CAT2(a, b)
 
 int PMG_SWEEP_CAT(pmg_sweep_dispatch_m, PMG_SWEEP_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
-                                                           double *out, double f1, double f2, cudaStream_t s, int *geom)
+                                                           double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
   switch (lv->degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
-  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US, PMG_SWEEP_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom);
+  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US, PMG_SWEEP_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom, part);
 #include "pmg_apply_sweep_tiles.inc"
 #undef PMG_SWEEP_CASE
     default: return PMG_ERR_UNSUPPORTED;

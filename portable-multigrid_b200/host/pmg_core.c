@@ -64,6 +64,15 @@ static int context_common(pmg_context **out, int device, int rank, int n_ranks, 
     memcpy(&id, nccl_id, sizeof(id));
     PMG_NCCL(ncclCommInitRank(&ctx->comm, n_ranks, id, rank));
     ctx->has_comm = 1;
+    /* PMG_HALO_OVERLAP=0 keeps the halo exchange on the compute stream, in front of the apply kernel */
+    const char *ov = getenv("PMG_HALO_OVERLAP");
+    if (!ov || atoi(ov) != 0) {
+      PMG_NCCL(ncclCommSplit(ctx->comm, 0, rank, &ctx->halo_comm, NULL));
+      PMG_CUDA(cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking));
+      PMG_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+      PMG_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+      ctx->overlap = 1;
+    }
   }
   *out = ctx;
   return PMG_OK;
@@ -90,6 +99,12 @@ int pmg_context_destroy(pmg_context *ctx)
   if (!ctx) return PMG_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->overlap) {
+    cudaStreamSynchronize(ctx->halo_stream);
+    ncclCommDestroy(ctx->halo_comm);
+    cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_halo);
+    cudaStreamDestroy(ctx->halo_stream);
+  }
   if (ctx->has_comm) ncclCommDestroy(ctx->comm);
   cudaFree(ctx->work); cudaFree(ctx->scalars); cudaFreeHost(ctx->h_scalars);
   cudaStreamDestroy(ctx->stream);
@@ -320,18 +335,23 @@ int pmg_vector_mean_value(const pmg_vector *x, double *result)
 /* ---- halo exchange ------------------------------------------------------------ */
 int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d)
 {
+  return pmg_halo_update_on(ctx, lay, d, ctx->comm, ctx->stream);
+}
+
+int pmg_halo_update_on(pmg_context *ctx, const pmg_layout *lay, double *d, ncclComm_t comm, cudaStream_t stream)
+{
   if (!ctx->has_comm || lay->gathered || !lay->active) return PMG_OK;
   const int p = lay->degree;
   const int64_t plane = lay->plane;
   PMG_NCCL(ncclGroupStart());
   if (lay->upper >= 0) {
     /* my top p owned planes -> upper neighbour's lower ghost layer; its first owned plane -> my upper ghost */
-    PMG_NCCL(ncclSend(d + plane * (lay->z_own_hi - p - lay->z0), (size_t)(plane * p), ncclDouble, lay->upper, ctx->comm, ctx->stream));
-    PMG_NCCL(ncclRecv(d + plane * (lay->z_own_hi - lay->z0), (size_t)plane, ncclDouble, lay->upper, ctx->comm, ctx->stream));
+    PMG_NCCL(ncclSend(d + plane * (lay->z_own_hi - p - lay->z0), (size_t)(plane * p), ncclDouble, lay->upper, comm, stream));
+    PMG_NCCL(ncclRecv(d + plane * (lay->z_own_hi - lay->z0), (size_t)plane, ncclDouble, lay->upper, comm, stream));
   }
   if (lay->lower >= 0) {
-    PMG_NCCL(ncclSend(d + plane * (lay->z_own_lo - lay->z0), (size_t)plane, ncclDouble, lay->lower, ctx->comm, ctx->stream));
-    PMG_NCCL(ncclRecv(d, (size_t)(plane * p), ncclDouble, lay->lower, ctx->comm, ctx->stream));
+    PMG_NCCL(ncclSend(d + plane * (lay->z_own_lo - lay->z0), (size_t)plane, ncclDouble, lay->lower, comm, stream));
+    PMG_NCCL(ncclRecv(d, (size_t)(plane * p), ncclDouble, lay->lower, comm, stream));
   }
   PMG_NCCL(ncclGroupEnd());
   pmg_count_launch(1);

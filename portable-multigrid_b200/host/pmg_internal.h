@@ -57,6 +57,11 @@ struct pmg_context {
   cudaStream_t stream;
   ncclComm_t comm;
   int has_comm;
+  /* halo exchange overlapped with the interior chunks of the apply (pmg_operator.c): its own stream and communicator */
+  cudaStream_t halo_stream;
+  ncclComm_t halo_comm;
+  cudaEvent_t ev_ready, ev_halo;
+  int overlap;
   int64_t coarse_threshold;
   double *work;      /* device: reduction workspace */
   double *scalars;   /* device: small scalar slots */
@@ -120,7 +125,10 @@ int pmg_layout_make(pmg_context *ctx, int dim, int degree, int nx, int ny, int n
 int pmg_layout_same(const pmg_layout *a, const pmg_layout *b);
 int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector **v);
 int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d);
+int pmg_halo_update_on(pmg_context *ctx, const pmg_layout *lay, double *d, ncclComm_t comm, cudaStream_t stream);
 int pmg_allreduce_sum(pmg_context *ctx, double *dev_scalar, int count);
+/* ghost update of u + fused apply; the exchange overlaps the interior z-chunks when the launch splits (pmg_operator.c) */
+int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1, double f2);
 int pmg_chebyshev_estimate(pmg_chebyshev *s);
 /* fused smoother: u <- smooth(u, rhs); zero_guess => u is taken as 0 on entry.  tmp: work vector.
    On return *result points at the vector that holds the smoothed iterate (u or tmp). */

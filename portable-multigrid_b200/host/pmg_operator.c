@@ -112,15 +112,33 @@ static int check_vec(const pmg_operator *op, const pmg_vector *v, const char *wh
   return PMG_OK;
 }
 
-static int apply_mode(const pmg_operator *op, int mode, pmg_vector *dst, const pmg_vector *src, const pmg_vector *b,
-                      const pmg_vector *xold, double f1, double f2)
+/* ghost update of u followed by the fused apply (every operator application of the path goes through here) */
+int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1, double f2)
 {
   pmg_context *ctx = op->ctx;
   if (!op->lay.active) return PMG_OK;
   /* src.update_ghost_values() (:661); there is no compress(add): the kernel owns complete rows */
-  PMG_CHECK(pmg_halo_update(ctx, &src->lay, src->d));
-  PMG_CHECK(pmgk_apply(&op->lv, mode, src->d, b ? b->d : NULL, xold ? xold->d : NULL, dst->d, f1, f2, ctx->stream));
-  return PMG_OK;
+  const int slab = ctx->has_comm && !op->lay.gathered;
+  if (slab && ctx->overlap && pmgk_apply_splits(&op->lv, mode)) {
+    /* the reference's overlap of communication and computation (:635-657: ghost_start, interior cells, ghost_finish,
+       boundary cells), here for the z-chunks of the launch: the chunks that read no ghost plane run while the ghost planes
+       travel on the halo stream / communicator; the first and the last chunk follow.  Event fork / join, capturable. */
+    PMG_CUDA(cudaEventRecord(ctx->ev_ready, ctx->stream));
+    PMG_CUDA(cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_ready, 0));
+    PMG_CHECK(pmg_halo_update_on(ctx, &op->lay, u, ctx->halo_comm, ctx->halo_stream));
+    PMG_CUDA(cudaEventRecord(ctx->ev_halo, ctx->halo_stream));
+    PMG_CHECK(pmgk_apply_part(&op->lv, mode, u, b, xold, out, f1, f2, PMGK_PART_INTERIOR, ctx->stream));
+    PMG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+    return pmgk_apply_part(&op->lv, mode, u, b, xold, out, f1, f2, PMGK_PART_BOUNDARY, ctx->stream);
+  }
+  PMG_CHECK(pmg_halo_update(ctx, &op->lay, u));
+  return pmgk_apply(&op->lv, mode, u, b, xold, out, f1, f2, ctx->stream);
+}
+
+static int apply_mode(const pmg_operator *op, int mode, pmg_vector *dst, const pmg_vector *src, const pmg_vector *b,
+                      const pmg_vector *xold, double f1, double f2)
+{
+  return pmg_apply_with_halo(op, mode, src->d, b ? b->d : NULL, xold ? xold->d : NULL, dst->d, f1, f2);
 }
 
 int pmg_laplace_operator_vmult(const pmg_operator *op, pmg_vector *dst, const pmg_vector *src)

@@ -200,8 +200,7 @@ int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs,
   if (zero_guess) {
     PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0 / theta, rhs->d, cur->d, ctx->stream)); /* x1 in cur, x0 = 0 */
   } else {
-    PMG_CHECK(pmg_halo_update(ctx, &cur->lay, cur->d));
-    PMG_CHECK(pmgk_apply(&op->lv, PMGK_CHEB_FIRST, cur->d, rhs->d, NULL, other->d, 0.0, 1.0 / theta, ctx->stream));
+    PMG_CHECK(pmg_apply_with_halo(op, PMGK_CHEB_FIRST, cur->d, rhs->d, NULL, other->d, 0.0, 1.0 / theta));
     pmg_vector *t = cur; cur = other; other = t; /* cur = x1, other = x0 */
     other_is_xold = 1;
   }
@@ -213,9 +212,7 @@ int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs,
       const double factor1 = rhokp * rhok, factor2 = 2.0 * rhokp / delta;
       rhok = rhokp;
       /* x_{k+2} = x_{k+1} + f1 (x_{k+1} - x_k) + f2 Dinv (rhs - A x_{k+1}), written over x_k */
-      PMG_CHECK(pmg_halo_update(ctx, &cur->lay, cur->d));
-      PMG_CHECK(pmgk_apply(&op->lv, PMGK_CHEB_STEP, cur->d, rhs->d, other_is_xold ? other->d : NULL, other->d, factor1, factor2,
-                           ctx->stream));
+      PMG_CHECK(pmg_apply_with_halo(op, PMGK_CHEB_STEP, cur->d, rhs->d, other_is_xold ? other->d : NULL, other->d, factor1, factor2));
       pmg_vector *t = cur; cur = other; other = t;
       other_is_xold = 1;
     }
