@@ -64,9 +64,12 @@ static int context_common(pmg_context **out, int device, int rank, int n_ranks, 
     memcpy(&id, nccl_id, sizeof(id));
     PMG_NCCL(ncclCommInitRank(&ctx->comm, n_ranks, id, rank));
     ctx->has_comm = 1;
-    /* PMG_HALO_OVERLAP=0 keeps the halo exchange on the compute stream, in front of the apply kernel */
+    /* PMG_HALO_OVERLAP=1: halo exchange on its own stream / communicator, overlapped with the interior z-chunks of the apply
+       (pmg_operator.c).  OFF by default: measured on 2 B200s (profiles/r01_halo_overlap_2gpu.txt) the split launch is slower
+       -- fused step 0.321 against 0.271 ms, V-cycle 9.52 against 7.93 ms: the apply kernel fills every SM, so the NCCL kernel
+       only gets in when the interior launch drains, and the second launch + two event hops are added on top. */
     const char *ov = getenv("PMG_HALO_OVERLAP");
-    if (!ov || atoi(ov) != 0) {
+    if (ov && atoi(ov) != 0) {
       PMG_NCCL(ncclCommSplit(ctx->comm, 0, rank, &ctx->halo_comm, NULL));
       PMG_CUDA(cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking));
       PMG_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
