@@ -203,7 +203,10 @@ PMG_HD constexpr int pmg_sweep_canon(int i, int j)
 // SG: the y lines of phase 1 and the x lines of phase 2 are cut into SG segments of cells, each marched by its own thread (a
 // segment starts from the partial cell before it, as the tile's first segment starts from the halo cell): SG x the work items
 // in the two phases that fill only half of the CTA, for one partial cell more per line and segment
-template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1>
+// RL: 1 = the cell loops of phases 1 and 2 stay rolled (one copy of the cell body instead of BY resp. BX copies): the
+// steady-state loop of the Q4 apply kernel is 67 KB of code unrolled (tools/sass_regions.py), more than the instruction
+// caches hold, and ncu attributes 10-13 % of the stall samples to instruction fetch (profiles/r01_v5_apply_q4_ncu.md)
+template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1, int RL = 0>
 struct PmgSweepTile {
   static constexpr int N1 = P + 1;
   static PMG_HD int mode_of(const PmgSweepParams<P> &p) { return FM >= 0 ? FM : p.mode; }
@@ -464,7 +467,7 @@ struct PmgSweepTile {
       } else {
         v0 = dir_lo ? 0.0 : PMG_AROW(P);
       }
-#pragma unroll
+#pragma unroll (RL ? 1 : BYS)
       for (int ci = 0; ci < BYS; ++ci) {
         const int c = c_lo + ci;
         if (c < t.ncy) {
@@ -473,9 +476,12 @@ struct PmgSweepTile {
 #pragma unroll
           for (int kk = 0; kk < N1; ++kk) { sc[kk] = 0.0; sd[kk] = 0.0; }
           sc[0] = cc; sd[0] = cd;
+          // rolled: the parity of the cell's first row is a run-time value when P is odd; pick the two row bases once per cell
+          const double *Ac0 = (((P + c * P) & 1) ? Ao : Ae) + (P + c * P) * XPA;
+          const double *Ac1 = (((P + c * P) & 1) ? Ae : Ao) + (P + c * P) * XPA;
 #pragma unroll
           for (int j = 0; j < N1; ++j) {
-            if (j > 0) vj = PMG_AROW(P + c * P + j);
+            if (j > 0) vj = ((j & 1) ? Ac1 : Ac0)[j * XPA];
             if (j == P && dir_hi && t.cy0 + c == p.ny - 1) vj = 0.0;
 #pragma unroll
             for (int kk = 0; kk < N1; ++kk) {
@@ -555,7 +561,7 @@ struct PmgSweepTile {
       } else {
         c0 = Cr[P]; d0 = Dr[P];
       }
-#pragma unroll
+#pragma unroll (RL ? 1 : BXS)
       for (int ii = 0; ii < BXS; ++ii) {
         const int i = i_lo + ii;
         if (i < t.ncx) {
