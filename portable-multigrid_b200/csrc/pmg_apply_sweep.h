@@ -206,7 +206,10 @@ PMG_HD constexpr int pmg_sweep_canon(int i, int j)
 // RL: 1 = the cell loops of phases 1 and 2 stay rolled (one copy of the cell body instead of BY resp. BX copies): the
 // steady-state loop of the Q4 apply kernel is 67 KB of code unrolled (tools/sass_regions.py), more than the instruction
 // caches hold, and ncu attributes 10-13 % of the stall samples to instruction fetch (profiles/r01_v5_apply_q4_ncu.md)
-template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1, int RL = 0>
+// A2: 1 = the phase-2 items sit on the lower half of the CTA's threads in even steps and on the upper half in odd steps.  With
+// 4 warps per CTA warp w runs on SM sub-partition w; phases 1 and 2 otherwise both load warps 0 and 1, whose FP64 pipes then
+// carry 2.5 x the work of sub-partition 2 and 5.7 x that of sub-partition 3 (DESIGN.md "sub-partition balance")
+template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1, int RL = 0, int A2 = 0>
 struct PmgSweepTile {
   static constexpr int N1 = P + 1;
   static PMG_HD int mode_of(const PmgSweepParams<P> &p) { return FM >= 0 ? FM : p.mode; }
@@ -241,6 +244,7 @@ struct PmgSweepTile {
   static constexpr int IT2 = (RW * NPS * SG + NT - 1) / NT; // phase-2 items per thread
   static constexpr int NT2 = ((RW * NPS * SG + 31) / 32 * 32 < NT) ? (RW * NPS * SG + 31) / 32 * 32 : NT; // threads that can hold a phase-2 item in round 0
   static_assert(SG >= 1 && SG <= 2 && SG <= BX && SG <= BY, "one or two segments per line (seed2 holds one hand-over)");
+  static_assert(!(A2 && SG > 1), "A2 moves the phase-2 items off the first NT2 threads, which is where the SG > 1 barrier expects them");
   static constexpr int NCOL = (CW * RW + NT - 1) / NT; // dof columns per thread in phase 3
   static_assert(NT % 32 == 0, "whole warps: the last one is the cp.async loader");
   static_assert(CW <= 255 && RW <= 255, "column coordinates are packed into 8 bits each (ThreadState::info)");
@@ -259,7 +263,7 @@ struct PmgSweepTile {
     double uP[NCOL];    // u of that plane (epilogue input of the next layer's plane 0)
     double dinv[NCOL][P]; // inverse diagonal of the column's planes k = 0..P-1 of an interior layer (CHEB modes, table)
     int info[NCOL];     // ox | oy << 8 | Dirichlet-in-xy << 16 | x position type << 20 | y position type << 24; -1 = none
-    int item2[IT2];     // phase-2 item: row | plane << 16 | segment << 24; -1 = none
+    int item2[A2 ? 2 : 1][IT2]; // phase-2 item: row | plane << 16 | segment << 24; -1 = none ([1]: the odd steps' item when A2)
     double seed2[SG > 1 ? IT2 : 1][4]; // SG > 1: what a phase-2 item reads before the in-place sweep starts (phase2_seed)
   };
 
@@ -321,11 +325,15 @@ struct PmgSweepTile {
       }
     }
 #pragma unroll
-    for (int i = 0; i < IT2; ++i) { // rows fastest: the lanes of a warp walk down a column of the buffer
-      const int item = tid + i * NT;
-      const int kk = item / t.rows;
-      const int seg = kk / NPS, k = kk - seg * NPS;
-      st.item2[i] = (seg < SG) ? ((item - kk * t.rows) | (k << 16) | (seg << 24)) : -1;
+    for (int a = 0; a < (A2 ? 2 : 1); ++a) {
+      const int tid2 = (a == 0) ? tid : (tid + NT / 2) % NT; // odd steps: the other half of the CTA's warps goes first
+#pragma unroll
+      for (int i = 0; i < IT2; ++i) { // rows fastest: the lanes of a warp walk down a column of the buffer
+        const int item = tid2 + i * NT;
+        const int kk = item / t.rows;
+        const int seg = kk / NPS, k = kk - seg * NPS;
+        st.item2[a][i] = (seg < SG) ? ((item - kk * t.rows) | (k << 16) | (seg << 24)) : -1;
+      }
     }
   }
 
@@ -504,11 +512,12 @@ struct PmgSweepTile {
   // overwrites is read first (phase2_seed; the phase-2 threads then meet at a barrier of their own): a later segment's start --
   // the partial sums of the cell before it and the (c, d) of the vertex it starts at -- and an earlier segment's last input, the
   // (c, d) of the vertex where the next segment starts.  seed2 = {cg, cm, c0, d0} resp. {c_end, d_end, -, -}.
-  static PMG_HD void phase2_seed(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *Cb, const double *Db, int npl)
+  static PMG_HD void phase2_seed(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, const double *Cb, const double *Db, int npl,
+                                 int alt = 0)
   {
 #pragma unroll
     for (int it = 0; it < (SG > 1 ? IT2 : 0); ++it) {
-      const int item = st.item2[it];
+      const int item = (A2 && alt) ? st.item2[A2 ? 1 : 0][it] : st.item2[0][it];
       if (item < 0) continue;
       const int r = item & 0xFFFF, k = (item >> 16) & 0xFF, seg = item >> 24;
       if (k >= npl) continue;
@@ -532,11 +541,12 @@ struct PmgSweepTile {
     }
   }
 
-  static PMG_HD void phase2(const PmgSweepParams<P> &p, const TileGeom &t, const ThreadState &st, double *Cb, double *Db, int npl)
+  static PMG_HD void phase2(const PmgSweepParams<P> &p, const TileGeom &t, const ThreadState &st, double *Cb, double *Db, int npl,
+                            int alt = 0)
   {
 #pragma unroll
     for (int it = 0; it < IT2; ++it) {
-      const int item = st.item2[it];
+      const int item = (A2 && alt) ? st.item2[A2 ? 1 : 0][it] : st.item2[0][it];
       if (item < 0) continue;
       const int r = item & 0xFFFF, k = (item >> 16) & 0xFF, seg = (SG == 1) ? 0 : item >> 24;
       if (k >= npl) continue;
@@ -799,7 +809,8 @@ struct PmgSweepTile {
     ex.sync();
 
     int cur = 1;
-    for (int cz = cz_first; cz < cz_end; cz += LZ) {
+    int alt = 0; // A2: which half of the CTA's warps holds the phase-2 items in this step
+    for (int cz = cz_first; cz < cz_end; cz += LZ, alt ^= 1) {
       double *A = smem + cur * ABUF;
       int nlay = cz_end - cz; if (nlay > LZ) nlay = LZ;
       int nnext = cz_end - (cz + LZ); if (nnext > LZ) nnext = LZ;
@@ -817,11 +828,11 @@ struct PmgSweepTile {
       par_u[cur] ^= 1;
       ex.sync();
       if (SG > 1) { // the phase-2 threads read what another segment of their row overwrites, then meet at their own barrier
-        ex.for_each_thread([&](int, ThreadState &st) { phase2_seed(p, t, st, Cb, Db, nlay * P); });
+        ex.for_each_thread([&](int, ThreadState &st) { phase2_seed(p, t, st, Cb, Db, nlay * P, alt); });
         ex.sync_some(NT2);
       }
       ex.for_each_thread([&](int tid, ThreadState &st) {
-        phase2(p, t, st, Cb, Db, nlay * P);
+        phase2(p, t, st, Cb, Db, nlay * P, alt);
         if (tid >= NT - 32) pmg_sweep_cp_async_wait_all(); // the loader warp's copies (E for phase 3, u rows for the next step)
       });
       ex.sync();

@@ -17,11 +17,11 @@ struct PmgSweepDeviceExec {
 
 // chunk_first, chunk_stride: the launch's CTAs work on z-chunks chunk_first + i * chunk_stride (all chunks: 0, 1; the two
 // chunks that touch the slab's ghost planes: 0, n_chunks - 1; the others: 1, 1)
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL>
 __global__ void __launch_bounds__(NT, MINB)
 pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>;
   extern __shared__ __align__(128) double pmg_sweep_smem[];
   PmgSweepDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -49,11 +49,19 @@ void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int min_c
   *layers_per_chunk = (layers + best_c - 1) / best_c;
 }
 
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM>
+// Per-mode overrides of the tile table (csrc/pmg_apply_sweep_tiles.inc).  The plain apply of Q4 keeps the cell loops of the y
+// and x sweeps rolled (RL = 1): 106 registers instead of 163, so 4 CTAs of its 52.6 KB fit an SM instead of 3 -- measured on
+// B200 at 100 M DoFs: 0.825 ms against 0.879 ms (122 against 114 GDoF/s, profiles/r01_v6_ablation_experiment.txt).  The fused
+// modes stay at 3 CTAs per SM by shared memory and gain nothing from rolled loops; Q2 / Q3 / Q5 measured 3-5 % slower rolled
+// (profiles/r01_v6_rolled_loops_experiment.txt).
+template <int P, int FM> struct PmgSweepModeTune { static constexpr int roll = 0, min_ctas = 0; };
+template <> struct PmgSweepModeTune<4, PMG_MODE_APPLY> { static constexpr int roll = 1, min_ctas = 4; };
+
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL>
 int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1,
                  double f2, cudaStream_t stream, int *geom, int part)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
   p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
@@ -69,9 +77,9 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
   static int configured = 0;
   static int ctas_per_sm = 1;
   if (!configured) {
-    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem_bytes));
-    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM>, NT,
+    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>, NT,
                                                                  smem_bytes));
     if (ctas_per_sm < 1) return PMG_ERR_CUDA;
     configured = 1;
@@ -93,7 +101,7 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
   const int grid = p.tiles_x * p.tiles_y * chunk_count;
   if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
   if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
-  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM><<<grid, NT, smem_bytes, stream>>>(p, chunk_first, chunk_stride);
+  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL><<<grid, NT, smem_bytes, stream>>>(p, chunk_first, chunk_stride);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
@@ -109,7 +117,8 @@ int PMG_SWEEP_CAT(pmg_sweep_dispatch_m, PMG_SWEEP_TU_MODE)(const pmgk_level *lv,
 {
   switch (lv->degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
-  case P: return launch_sweep<P, BX, BY, LZ, NT, MINB, US, PMG_SWEEP_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom, part);
+  case P: return launch_sweep<P, BX, BY, LZ, NT, (PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::min_ctas ? PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::min_ctas : MINB), \
+                              US, PMG_SWEEP_TU_MODE, PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::roll>(lv, u, b, xold, out, f1, f2, s, geom, part);
 #include "pmg_apply_sweep_tiles.inc"
 #undef PMG_SWEEP_CASE
     default: return PMG_ERR_UNSUPPORTED;

@@ -226,17 +226,20 @@ def test_emulated_sweep_with_two_segments_per_line(p, small, emu, oracle):
 
 
 @pytest.mark.parametrize("p", range(1, 9))
-def test_emulated_sweep_with_rolled_cell_loops(p, emu, oracle):
+@pytest.mark.parametrize("small", [4, 5])
+def test_emulated_sweep_with_rolled_cell_loops(p, small, emu, oracle):
     """RL = 1 (csrc/pmg_apply_sweep.h): the cell loops of the y and x sweeps stay rolled (smaller code); for odd degrees the
-    parity of a cell's first staged row is then a run-time value.  Odd and even cell counts per tile, all epilogues."""
-    n = (5, 5, 3) if p < 5 else (3, 4, 2)
+    parity of a cell's first staged row is then a run-time value.  Odd and even cell counts per tile, all epilogues.
+    small = 5: A2 = 1 as well, the x sweep's work items move to the other half of the CTA's threads in every second step (several
+    steps per chunk, so both assignments run)."""
+    n = (5, 5, 5) if p < 5 else (3, 4, 3)
     for faces in (0x3F, 0x2A):
         mf = oracle.MatrixFree(3, p, n, faces=faces)
         u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (81, 82, 83))
         Au, dinv = mf.vmult(u), mf.compute_diagonal()
-        assert rel_l2(emu_apply(emu, p, n, u, small=4, chunks=2, faces=faces), Au) < 1e-13
+        assert rel_l2(emu_apply(emu, p, n, u, small=small, chunks=2, faces=faces), Au) < 1e-13
         ref = u + 0.3 * (u - xo) + 0.7 * dinv * (b - Au)
-        assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.7, small=4, faces=faces), ref) < 1e-13
+        assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.7, small=small, faces=faces), ref) < 1e-13
 
 
 # ---- variable-coefficient tile program (csrc/pmg_apply_var.h) under the host emulator ---------------------
