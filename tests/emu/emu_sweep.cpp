@@ -5,7 +5,9 @@
 // fused epilogues against the oracle without a GPU.  Not part of libpmg.so: the product has no CPU path.
 #include <vector>
 #include <cstring>
+#include <type_traits>
 #include "pmg_apply_sweep.h"
+#include "pmg_apply_sweep_pipe.h"
 
 template <class Tile>
 struct SweepHostExec {
@@ -22,13 +24,14 @@ struct SweepHostExec {
 
 static bool g_reverse = false;
 
-template <int P, int BX, int BY, int LZ, int NT, int US = 1, int SG = 1, int RL = 0, int A2 = 0>
+template <int P, int BX, int BY, int LZ, int NT, int US = 1, int SG = 1, int RL = 0, int A2 = 0, int PL = 0>
 static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
                      int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG, RL, A2>;
+  // PL: the pipelined variant (csrc/pmg_apply_sweep_pipe.h): two groups of NT threads each
+  using Tile = std::conditional_t<PL != 0, PmgSweepPipe<P, BX, BY, LZ, NT, US, -1, RL>, PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG, RL, A2>>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -76,14 +79,28 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
 // several items per thread and several columns per thread; 0 = the tiles pmg_apply.cu launches;
 // 2, 3 = small tiles with two segments per line (SG = 2), 3 with the threads of every phase run in descending order;
 // 4 = small tiles with the cell loops of phases 1 and 2 rolled (RL = 1); 5 = small tiles, phase-2 items alternating between
-// the two halves of the CTA from step to step (A2 = 1), rolled loops for the odd degrees
+// the two halves of the CTA from step to step (A2 = 1), rolled loops for the odd degrees; 6, 7 = the pipelined variant
+// (pmg_apply_sweep_pipe.h) on small tiles, 7 with the threads run in descending order (the z-sweep group before the y/x group)
 extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, unsigned faces, int z0, int nzl,
                          int cz_lo, int cz_hi, int z_own_lo, int z_own_hi, int n_chunks, const double *M,
                          const double *K, const double *h, int mode, const double *u, const double *b,
                          const double *xold, double *out, double f1, double f2, const double *dinv_vec,
                          const double *dinv_tab)
 {
-  g_reverse = (small_tiles == 3);
+  g_reverse = (small_tiles == 3 || small_tiles == 7);
+  if (small_tiles == 6 || small_tiles == 7) {
+    switch (degree) {
+      case 1: sweep_go<1, 3, 2, 3, 32, 1, 1, 0, 0, 1>(ARGS); return 0;
+      case 2: sweep_go<2, 2, 3, 2, 32, 0, 1, 0, 0, 1>(ARGS); return 0;
+      case 3: sweep_go<3, 2, 3, 1, 32, 1, 1, 1, 0, 1>(ARGS); return 0;
+      case 4: sweep_go<4, 3, 2, 1, 64, 1, 1, 1, 0, 1>(ARGS); return 0;
+      case 5: sweep_go<5, 2, 3, 1, 32, 0, 1, 0, 0, 1>(ARGS); return 0;
+      case 6: sweep_go<6, 2, 1, 1, 32, 1, 1, 0, 0, 1>(ARGS); return 0;
+      case 7: sweep_go<7, 1, 2, 1, 32, 1, 1, 1, 0, 1>(ARGS); return 0;
+      case 8: sweep_go<8, 1, 2, 1, 64, 0, 1, 0, 0, 1>(ARGS); return 0;
+    }
+    return -3;
+  }
   if (small_tiles == 5) {
     switch (degree) {
       case 1: sweep_go<1, 3, 2, 3, 32, 1, 1, 1, 1>(ARGS); return 0;

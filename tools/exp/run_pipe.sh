@@ -1,0 +1,20 @@
+#!/bin/bash
+# Pipelined apply kernel (csrc/pmg_apply_sweep_pipe.h): build, time and self-check against the plain kernel -> gpurun_out/exp_pipe.txt
+#   gpurun --timeout 300 -- 'bash tools/exp/run_pipe.sh'
+cd "$(dirname "$0")" || exit 1
+mkdir -p bin ../../gpurun_out
+export EXP_SRC=exp_pipe.cu
+[ -x bin/pipe_q4_f0 ] || {
+  ./build_exp.sh pipe_q4_f0 4 4 4 1 128 2 -DC_US=1 -DC_FM=0 -DC_RL=1
+  ./build_exp.sh pipe_q4_f3 4 4 4 1 128 1 -DC_US=1 -DC_FM=3 -DC_RL=1
+  ./build_exp.sh pipe_q2_f0 2 8 8 2 128 2 -DC_US=1 -DC_FM=0
+  ./build_exp.sh pipe_q2_f3 2 8 8 2 128 2 -DC_US=1 -DC_FM=3
+  ./build_exp.sh pipe_q3_f0 3 6 5 1 128 2 -DC_US=0 -DC_FM=0
+  ./build_exp.sh pipe_q3_f3 3 6 5 1 128 2 -DC_US=0 -DC_FM=3
+  ./build_exp.sh pipe_q1_f0 1 16 16 4 128 2 -DC_US=0 -DC_FM=0
+}
+O=../../gpurun_out/exp_pipe.txt
+for b in pipe_q4_f0 pipe_q4_f3 pipe_q2_f0 pipe_q2_f3 pipe_q3_f0 pipe_q3_f3 pipe_q1_f0; do
+  timeout 40 ./bin/$b 0 5 >> $O 2>&1 || echo "$b failed ($?)" >> $O
+done
+cat $O
