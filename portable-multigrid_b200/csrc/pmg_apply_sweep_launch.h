@@ -2,6 +2,8 @@
 // epilogue mode.  Included by pmg_apply_sweep_m{0,1,2,3}.cu, each of which defines PMG_SWEEP_TU_MODE (the PmgApplyMode the
 // translation unit is compiled for) and so provides pmg_sweep_dispatch_m<mode>(); four translation units compile in parallel.
 #include "pmg_apply_sweep.h"
+#include "pmg_apply_sweep_pipe.h"
+#include <type_traits>
 #include "pmg_cuda_common.h"
 #include "pmg_kernels.h"
 
@@ -22,6 +24,21 @@ __global__ void __launch_bounds__(NT, MINB)
 pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
   using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>;
+  extern __shared__ __align__(128) double pmg_sweep_smem[];
+  PmgSweepDeviceExec<Tile> ex;
+  const int b = blockIdx.x;
+  const int tile_x = b % p.tiles_x;
+  const int tile_y = (b / p.tiles_x) % p.tiles_y;
+  const int chunk = chunk_first + (b / (p.tiles_x * p.tiles_y)) * chunk_stride;
+  Tile::run(p, ex, pmg_sweep_smem, tile_x, tile_y, chunk);
+}
+
+// the pipelined variant (csrc/pmg_apply_sweep_pipe.h, opt-in: PMG_TILE_VARIANT=4): two groups of NG threads per CTA
+template <int P, int BX, int BY, int LZ, int NG, int MINB, int US, int FM, int RL>
+__global__ void __launch_bounds__(2 * NG, MINB)
+pmg_sweep_pipe_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
+{
+  using Tile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL>;
   extern __shared__ __align__(128) double pmg_sweep_smem[];
   PmgSweepDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -57,11 +74,14 @@ void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int min_c
 template <int P, int FM> struct PmgSweepModeTune { static constexpr int roll = 0, min_ctas = 0; };
 template <> struct PmgSweepModeTune<4, PMG_MODE_APPLY> { static constexpr int roll = 1, min_ctas = 4; };
 
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL>
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL, bool PIPE = false>
 int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1,
                  double f2, cudaStream_t stream, int *geom, int part)
 {
-  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>;
+  using Tile = std::conditional_t<PIPE, PmgSweepPipe<P, BX, BY, LZ, NT, US, FM, RL>, PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>>;
+  void (*kernel)(const PmgSweepParams<P>, int, int);
+  if constexpr (PIPE) kernel = pmg_sweep_pipe_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>;
+  else kernel = pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
   p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
@@ -77,10 +97,8 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
   static int configured = 0;
   static int ctas_per_sm = 1;
   if (!configured) {
-    PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        smem_bytes));
-    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>, NT,
-                                                                 smem_bytes));
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, Tile::NT, smem_bytes));
     if (ctas_per_sm < 1) return PMG_ERR_CUDA;
     configured = 1;
   }
@@ -99,12 +117,27 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
     else { chunk_stride = p.n_chunks - 1; chunk_count = 2; }
   }
   const int grid = p.tiles_x * p.tiles_y * chunk_count;
-  if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
+  if (geom) { geom[0] = grid; geom[1] = Tile::NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
   if (((uintptr_t)u | (uintptr_t)b | (uintptr_t)xold) & 15) return PMG_ERR_ARG; /* bulk copies: 16-byte aligned vectors */
-  pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL><<<grid, NT, smem_bytes, stream>>>(p, chunk_first, chunk_stride);
+  kernel<<<grid, Tile::NT, smem_bytes, stream>>>(p, chunk_first, chunk_stride);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
+}
+
+// the pipelined variant with the same tile, NG = the table's thread count per group; CTAs per SM as shared memory allows
+template <int P, int BX, int BY, int LZ, int NG, int US, int FM>
+int launch_sweep_pipe(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
+                      cudaStream_t stream, int *geom, int part)
+{
+  if constexpr (P <= 5) {
+    constexpr int RL = (P >= 4); // rolled cell loops: the two groups' register budgets add up
+    using PipeTile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL>;
+    constexpr int minb = (PipeTile::smem_doubles(FM != PMG_MODE_APPLY) * 8 + 1024 <= 113 * 1024) ? 2 : 1;
+    return launch_sweep<P, BX, BY, LZ, NG, minb, US, FM, RL, true>(lv, u, b, xold, out, f1, f2, stream, geom, part);
+  } else {
+    return PMG_ERR_UNSUPPORTED;
+  }
 }
 
 } // namespace
@@ -115,6 +148,15 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
 int PMG_SWEEP_CAT(pmg_sweep_dispatch_m, PMG_SWEEP_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
                                                            double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
+  if (lv->tile_variant == 4) { /* opt-in: the pipelined variant; degrees 1..5 (above, its buffers do not fit shared memory) */
+    switch (lv->degree) {
+#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
+  case P: if (P <= 5) return launch_sweep_pipe<P, BX, BY, LZ, NT, US, PMG_SWEEP_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom, part); break;
+#include "pmg_apply_sweep_tiles.inc"
+#undef PMG_SWEEP_CASE
+      default: break;
+    }
+  }
   switch (lv->degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
   case P: return launch_sweep<P, BX, BY, LZ, NT, (PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::min_ctas ? PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::min_ctas : MINB), \

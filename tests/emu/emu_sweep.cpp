@@ -153,6 +153,14 @@ extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, un
     }
     return -3;
   }
+  if (small_tiles == 8) { // the tiles pmg_apply.cu launches, cell loops rolled (what the Q4 plain apply ships with)
+    switch (degree) {
+#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) case P: sweep_go<P, BX, BY, LZ, NT, US, 1, 1>(ARGS); return 0;
+#include "pmg_apply_sweep_tiles.inc"
+#undef PMG_SWEEP_CASE
+    }
+    return -3;
+  }
   switch (degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) case P: sweep_go<P, BX, BY, LZ, NT, US>(ARGS); return 0;
 #include "pmg_apply_sweep_tiles.inc"

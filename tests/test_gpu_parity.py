@@ -3,6 +3,8 @@
 Tolerances are the ones BASELINE.json's north_star states: operator apply <= 1e-12 relative in
 l2, identical CG / V-cycle iteration counts, residual histories <= 1e-10 relative.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -14,7 +16,12 @@ APPLY_TOL = 1e-12
 HISTORY_TOL = 1e-10
 
 
-@pytest.fixture(autouse=True, params=["auto", "sweep", "celltile"])
+# PMG_TEST_PIPE=1 adds the pipelined line-marching kernel (PMG_TILE_VARIANT=4, csrc/pmg_apply_sweep_pipe.h: experimental,
+# emulator-verified, first GPU run pending) to the kernels every test is run with
+_KERNELS = ["auto", "sweep", "celltile"] + (["pipe"] if os.environ.get("PMG_TEST_PIPE") == "1" else [])
+
+
+@pytest.fixture(autouse=True, params=_KERNELS)
 def apply_kernel(request, monkeypatch):
     """Every test runs with the library's default choice of apply kernel (line-marching kernel for large levels, cell-tile
     kernel for small ones) and with each of the two forced: the meshes here are small, so the default alone would never
@@ -22,7 +29,7 @@ def apply_kernel(request, monkeypatch):
     if request.param == "auto":
         monkeypatch.delenv("PMG_TILE_VARIANT", raising=False)
     else:
-        monkeypatch.setenv("PMG_TILE_VARIANT", "1" if request.param == "sweep" else "2")
+        monkeypatch.setenv("PMG_TILE_VARIANT", {"sweep": "1", "celltile": "2", "pipe": "4"}[request.param])
     return request.param
 
 

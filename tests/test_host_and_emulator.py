@@ -225,6 +225,17 @@ def test_emulated_sweep_with_two_segments_per_line(p, small, emu, oracle):
         assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.7, small=small, faces=faces), ref) < 1e-13
 
 
+@pytest.mark.parametrize("p", [2, 3, 4])
+def test_emulated_shipped_tiles_with_rolled_cell_loops(p, emu, oracle):
+    """The launch tiles of csrc/pmg_apply_sweep_tiles.inc with RL = 1 -- the configuration the Q4 plain apply is launched with
+    (PmgSweepModeTune, csrc/pmg_apply_sweep_launch.h) -- on a mesh wider than one tile in x and y."""
+    n = (9, 10, 3) if p < 4 else (6, 5, 3)
+    mf = oracle.MatrixFree(3, p, n)
+    u = splitmix_src(mf.n_dofs, salt=p)
+    out = emu_apply(emu, p, n, u, small=8, chunks=2)
+    assert not np.isnan(out).any() and rel_l2(out, mf.vmult(u)) < 1e-13
+
+
 @pytest.mark.parametrize("p", range(1, 9))
 @pytest.mark.parametrize("small", [4, 5])
 def test_emulated_sweep_with_rolled_cell_loops(p, small, emu, oracle):

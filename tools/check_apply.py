@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Quick GPU parity check of the line-marching apply kernel against the oracle without pytest / torch (seconds):
     python tools/check_apply.py [degree ...]        (default: 4)
-Forces the line-marching kernel (PMG_TILE_VARIANT=1), compares vmult with the oracle on two meshes and two Dirichlet
+Forces the line-marching kernel (PMG_TILE_VARIANT=1 unless set: 4 = its pipelined variant), compares vmult with the oracle on two meshes and two Dirichlet
 masks per degree, tolerance 1e-12 relative l2 (north_star)."""
 import os
 import sys
@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("portable-multigrid_b200/python", "oracle", "tests"):
     sys.path.insert(0, os.path.join(ROOT, p))
-os.environ["PMG_TILE_VARIANT"] = "1"
+os.environ.setdefault("PMG_TILE_VARIANT", "1")  # 4 = the pipelined variant
 import numpy as np
 import pmg_b200 as G
 import pyoracle as O
