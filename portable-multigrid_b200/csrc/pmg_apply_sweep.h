@@ -209,7 +209,11 @@ PMG_HD constexpr int pmg_sweep_canon(int i, int j)
 // A2: 1 = the phase-2 items sit on the lower half of the CTA's threads in even steps and on the upper half in odd steps.  With
 // 4 warps per CTA warp w runs on SM sub-partition w; phases 1 and 2 otherwise both load warps 0 and 1, whose FP64 pipes then
 // carry 2.5 x the work of sub-partition 2 and 5.7 x that of sub-partition 3 (DESIGN.md "sub-partition balance")
-template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1, int RL = 0, int A2 = 0>
+// EG: 1 = the fused modes read b and x_old straight from global memory in the z sweep (the loads of a dof column's planes are
+// issued before its z-sweep arithmetic) instead of staging them in shared memory: 18.5 KB less per CTA at Q4, and the loader warp
+// is free for u rows.  Round 1 measured direct epilogue loads slower at equal occupancy; the option exists for the configurations
+// where it buys a resident CTA (4 per SM for the fused step, 2 per SM for the pipelined variant).  Not yet measured.
+template <int P, int BX, int BY, int LZ, int NT_, int US = 0, int FM = -1, int SG = 1, int RL = 0, int A2 = 0, int EG = 0>
 struct PmgSweepTile {
   static constexpr int N1 = P + 1;
   static PMG_HD int mode_of(const PmgSweepParams<P> &p) { return FM >= 0 ? FM : p.mode; }
@@ -237,8 +241,8 @@ struct PmgSweepTile {
   // E loader: the CTA's last warp (idle in phase 1: NITEM1 <= NT - 32 for the shipped tiles), LD_LPR lanes per row
   static constexpr int LD_LPR = (CW - 1 <= 16) ? 16 : 32;
   static constexpr int LD_RPI = 32 / LD_LPR;  // rows per warp instruction
-  static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return (epilogue_inputs ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
-  static constexpr int SMEM_DOUBLES = BAR_OFFSET_EPI + NBAR;
+  static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return ((epilogue_inputs && !EG) ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
+  static constexpr int SMEM_DOUBLES = (EG ? BAR_OFFSET_APPLY : BAR_OFFSET_EPI) + NBAR;
   static constexpr int BXS = (BX + SG - 1) / SG, BYS = (BY + SG - 1) / SG; // cells per segment
   static constexpr int NITEM1 = XW * NPS * SG;
   static constexpr int IT2 = (RW * NPS * SG + NT - 1) / NT; // phase-2 items per thread
@@ -291,7 +295,7 @@ struct PmgSweepTile {
     t.nxodd = p.Nx & 1; t.plodd = (p.Nx & 1) & (p.Ny & 1);
     t.eA = (int64_t)((t.cy0 - 1) * P) * p.Nx + (t.cx0 - 1) * P;
     t.n_local = (int64_t)p.Nx * p.Ny * p.nzl;
-    t.has_e = (mode_of(p) != PMG_MODE_APPLY);
+    t.has_e = (mode_of(p) != PMG_MODE_APPLY) && !EG; // b / x_old staged in shared memory
     t.has_xo = (mode_of(p) == PMG_MODE_CHEB_STEP) && (p.xold != nullptr);
     return t;
   }
@@ -632,6 +636,12 @@ struct PmgSweepTile {
       const int ox = info & 0xFF, oy = (info >> 8) & 0xFF;
       const double *G = Cb + oy * XP + P + ox;
       const double *Mm = Db + oy * XP + P + ox;
+      const int64_t goff = glayer + (int64_t)oy * p.Nx + ox; // the column's dof in plane 0 of the layer
+      double bbv[P], xov[P];
+      if (EG && FULL && MODE != PMG_MODE_APPLY) { // direct epilogue inputs: issue the loads before the z-sweep arithmetic
+#pragma unroll
+        for (int k = 0; k < P; ++k) { bbv[k] = p.b[goff + k * plane]; xov[k] = has_xo ? p.xold[goff + k * plane] : 0.0; }
+      }
       double g[N1], m[N1];
       g[0] = st.gP[ci]; m[0] = st.mP[ci];
 #pragma unroll
@@ -648,7 +658,7 @@ struct PmgSweepTile {
       if (write) {
         const bool dirxy = (info >> 16) & 1;
         const int tbase = ((info >> 20) & 0xF) + T * ((info >> 24) & 0xF);
-        double *po = p.out + glayer + (int64_t)oy * p.Nx + ox;
+        double *po = p.out + goff;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           const int gz = cz * P + k;
@@ -661,10 +671,10 @@ struct PmgSweepTile {
             const int fl = (q & 1) & t.plodd;
             double uc = 0.0, bb = 0.0, xo = 0.0, dinv = 1.0;
             if (MODE != PMG_MODE_APPLY || dir) uc = (q == 0) ? st.uP[ci] : Uc[(q - 1) * APLANE + (sa ^ fl)];
-            if (MODE != PMG_MODE_APPLY) bb = Ec[q * EPLANE];
-            if (has_xo) xo = Ec[EBUF + q * EPLANE];
+            if (MODE != PMG_MODE_APPLY) bb = !EG ? Ec[q * EPLANE] : FULL ? bbv[k] : p.b[goff + k * plane];
+            if (has_xo) xo = !EG ? Ec[EBUF + q * EPLANE] : FULL ? xov[k] : p.xold[goff + k * plane];
             if (MODE >= PMG_MODE_CHEB_FIRST) {
-              if (p.dinv_vec) dinv = p.dinv_vec[glayer + (int64_t)oy * p.Nx + ox + k * plane];
+              if (p.dinv_vec) dinv = p.dinv_vec[goff + k * plane];
               else if (FULL) dinv = st.dinv[ci][k];
               else dinv = p.dinv_tab[tbase + T * T * pmg_sweep_pos_type<P>(gz, p.Nz)];
             }

@@ -13,13 +13,14 @@
 //     u staging    3 buffers: step s in buffer (s + 1) % 3 (the z sweep of step s - 1 still reads u while step s + 1 is staged)
 //     C/D          2 pairs
 //     b / x_old    2 boxes (fused modes)
-// Shared memory at Q4, 4 x 4 cell columns: 90 KB (APPLY), 127 KB (fused modes).
+// Shared memory at Q4, 4 x 4 cell columns: 90 KB (APPLY), 127 KB (fused modes; 90 KB with EG = 1: b / x_old read from global
+// memory by the Z group, whose load latency the YX group's arithmetic covers).
 #pragma once
 #include "pmg_apply_sweep.h"
 
-template <int P, int BX, int BY, int LZ, int NG, int US = 0, int FM = -1, int RL = 0>
+template <int P, int BX, int BY, int LZ, int NG, int US = 0, int FM = -1, int RL = 0, int EG = 0>
 struct PmgSweepPipe {
-  using Base = PmgSweepTile<P, BX, BY, LZ, NG, US, FM, 1, RL>;
+  using Base = PmgSweepTile<P, BX, BY, LZ, NG, US, FM, 1, RL, 0, EG>;
   using ThreadState = typename Base::ThreadState;
   using TileGeom = typename Base::TileGeom;
   static constexpr int NT = 2 * NG;
@@ -30,8 +31,8 @@ struct PmgSweepPipe {
   static constexpr int E_OFFSET = CD_OFFSET + 4 * CBUF; // box i: b at E_OFFSET + 2 i EBUF, x_old right after it
   static constexpr int BAR_OFFSET_APPLY = E_OFFSET, BAR_OFFSET_EPI = E_OFFSET + 4 * EBUF;
   static constexpr int NBAR = NA;                       // one mbarrier per u staging buffer
-  static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return (epilogue_inputs ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
-  static constexpr int SMEM_DOUBLES = BAR_OFFSET_EPI + NBAR;
+  static PMG_HD constexpr int smem_doubles(bool epilogue_inputs) { return ((epilogue_inputs && !EG) ? BAR_OFFSET_EPI : BAR_OFFSET_APPLY) + NBAR; }
+  static constexpr int SMEM_DOUBLES = (EG ? BAR_OFFSET_APPLY : BAR_OFFSET_EPI) + NBAR;
   static_assert(ABUF % 2 == 0 && CBUF % 2 == 0, "16-byte aligned staging buffers");
   static_assert(SMEM_DOUBLES * 8 <= 227 * 1024, "tile does not fit the 227 KB of shared memory of a CTA");
 

@@ -24,14 +24,14 @@ struct SweepHostExec {
 
 static bool g_reverse = false;
 
-template <int P, int BX, int BY, int LZ, int NT, int US = 1, int SG = 1, int RL = 0, int A2 = 0, int PL = 0>
+template <int P, int BX, int BY, int LZ, int NT, int US = 1, int SG = 1, int RL = 0, int A2 = 0, int PL = 0, int EG = 0>
 static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
                      int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
   // PL: the pipelined variant (csrc/pmg_apply_sweep_pipe.h): two groups of NT threads each
-  using Tile = std::conditional_t<PL != 0, PmgSweepPipe<P, BX, BY, LZ, NT, US, -1, RL>, PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG, RL, A2>>;
+  using Tile = std::conditional_t<PL != 0, PmgSweepPipe<P, BX, BY, LZ, NT, US, -1, RL, EG>, PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG, RL, A2, EG>>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -80,7 +80,9 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
 // 2, 3 = small tiles with two segments per line (SG = 2), 3 with the threads of every phase run in descending order;
 // 4 = small tiles with the cell loops of phases 1 and 2 rolled (RL = 1); 5 = small tiles, phase-2 items alternating between
 // the two halves of the CTA from step to step (A2 = 1), rolled loops for the odd degrees; 6, 7 = the pipelined variant
-// (pmg_apply_sweep_pipe.h) on small tiles, 7 with the threads run in descending order (the z-sweep group before the y/x group)
+// (pmg_apply_sweep_pipe.h) on small tiles, 7 with the threads run in descending order (the z-sweep group before the y/x group);
+// 8 = the shipped tiles with rolled loops; 9 = small tiles, b / x_old read from global memory in the z sweep (EG = 1);
+// 10 = the pipelined variant with EG = 1
 extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, unsigned faces, int z0, int nzl,
                          int cz_lo, int cz_hi, int z_own_lo, int z_own_hi, int n_chunks, const double *M,
                          const double *K, const double *h, int mode, const double *u, const double *b,
@@ -88,6 +90,22 @@ extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, un
                          const double *dinv_tab)
 {
   g_reverse = (small_tiles == 3 || small_tiles == 7);
+  if (small_tiles == 9 || small_tiles == 10) {
+#define PMG_EG_CASE(P, BX, BY, LZ, NT, US, RL) \
+  case P: if (small_tiles == 9) sweep_go<P, BX, BY, LZ, NT, US, 1, RL, 0, 0, 1>(ARGS); else sweep_go<P, BX, BY, LZ, NT, US, 1, RL, 0, 1, 1>(ARGS); return 0;
+    switch (degree) {
+      PMG_EG_CASE(1, 3, 2, 3, 32, 1, 0)
+      PMG_EG_CASE(2, 2, 3, 2, 32, 1, 0)
+      PMG_EG_CASE(3, 2, 3, 1, 32, 1, 1)
+      PMG_EG_CASE(4, 3, 2, 1, 64, 1, 1)
+      PMG_EG_CASE(5, 2, 3, 1, 32, 0, 0)
+      PMG_EG_CASE(6, 2, 1, 1, 32, 1, 0)
+      PMG_EG_CASE(7, 1, 2, 1, 32, 1, 1)
+      PMG_EG_CASE(8, 1, 2, 1, 64, 0, 0)
+    }
+#undef PMG_EG_CASE
+    return -3;
+  }
   if (small_tiles == 6 || small_tiles == 7) {
     switch (degree) {
       case 1: sweep_go<1, 3, 2, 3, 32, 1, 1, 0, 0, 1>(ARGS); return 0;

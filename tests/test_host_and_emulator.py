@@ -254,12 +254,13 @@ def test_emulated_sweep_with_rolled_cell_loops(p, small, emu, oracle):
 
 
 @pytest.mark.parametrize("p", range(1, 9))
-@pytest.mark.parametrize("small", [6, 7])
+@pytest.mark.parametrize("small", [6, 7, 9, 10])
 def test_emulated_pipelined_sweep(p, small, emu, oracle):
     """csrc/pmg_apply_sweep_pipe.h: the y/x sweeps of step s and the z sweep + epilogue of step s - 1 run on two thread groups of
     one CTA (three u staging buffers, two C/D pairs, two b / x_old boxes).  Enough layers for every buffer to be reused several
     times; chunked and unchunked; all epilogues incl. x_old overwritten in place; a slab with ghost planes.  small = 7 runs the
-    threads in descending order, i.e. the z-sweep group of a tick before its y/x group."""
+    threads in descending order, i.e. the z-sweep group of a tick before its y/x group.  small = 9 / 10: EG = 1 (b and x_old read
+    from global memory by the z sweep instead of being staged in shared memory) for the plain / the pipelined kernel."""
     n = (5, 4, 9) if p < 3 else (4, 3, 7) if p < 5 else (3, 2, 5)
     for faces in (0x3F, 0x15):
         mf = oracle.MatrixFree(3, p, n, faces=faces)

@@ -26,7 +26,10 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #ifndef C_A2
 #define C_A2 0
 #endif
-#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM, C_SG, C_RL, C_A2
+#ifndef C_EG
+#define C_EG 0
+#endif
+#define CFG C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM, C_SG, C_RL, C_A2, C_EG
 #define STR2(x) #x
 #define STR(x) STR2(x)
 #define CFGSTR STR(C_P) "," STR(C_BX) "," STR(C_BY) "," STR(C_LZ) "," STR(C_NT)
@@ -34,7 +37,7 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #ifndef MINB
 #define MINB 3
 #endif
-using Tile = PmgSweepPipe<C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM, C_RL>;
+using Tile = PmgSweepPipe<C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM, C_RL, C_EG>;
 using RefTile = PmgSweepTile<C_P, C_BX, C_BY, C_LZ, C_NT, C_US, C_FM, 1, 0>;
 struct Ex {
   Tile::ThreadState st;

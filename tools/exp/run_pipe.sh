@@ -12,9 +12,19 @@ export EXP_SRC=exp_pipe.cu
   ./build_exp.sh pipe_q3_f0 3 6 5 1 128 2 -DC_US=0 -DC_FM=0
   ./build_exp.sh pipe_q3_f3 3 6 5 1 128 2 -DC_US=0 -DC_FM=3
   ./build_exp.sh pipe_q1_f0 1 16 16 4 128 2 -DC_US=0 -DC_FM=0
+  # fused step with b / x_old read from global memory by the z sweep (EG = 1): 2 CTAs/SM for the pipelined kernel ...
+  ./build_exp.sh pipe_eg_q4_f3 4 4 4 1 128 2 -DC_US=1 -DC_FM=3 -DC_RL=1 -DC_EG=1
+  ./build_exp.sh pipe_eg_q2_f3 2 8 8 2 128 2 -DC_US=1 -DC_FM=3 -DC_EG=1
+  ./build_exp.sh pipe_eg_q3_f3 3 6 5 1 128 2 -DC_US=0 -DC_FM=3 -DC_EG=1
+  # ... and 4 CTAs/SM for the plain kernel (exp_sweep.cu: timing only), next to the shipped configuration
+  EXP_SRC=exp_sweep.cu ./build_exp.sh eg_q4_f3_m4 4 4 4 1 128 4 -DC_US=1 -DC_FM=3 -DC_RL=1 -DC_EG=1
+  EXP_SRC=exp_sweep.cu ./build_exp.sh eg_q2_f3_m4 2 8 8 2 128 4 -DC_US=1 -DC_FM=3 -DC_RL=1 -DC_EG=1
+  EXP_SRC=exp_sweep.cu ./build_exp.sh eg_q4_f3_m3 4 4 4 1 128 3 -DC_US=1 -DC_FM=3 -DC_EG=1
+  EXP_SRC=exp_sweep.cu ./build_exp.sh o_q4_base_f3 4 4 4 1 128 3 -DC_US=1 -DC_FM=3
+  EXP_SRC=exp_sweep.cu ./build_exp.sh a_q4_base_f0 4 4 4 1 128 3 -DC_US=1 -DC_FM=0
 }
 O=../../gpurun_out/exp_pipe.txt
-for b in pipe_q4_f0 pipe_q4_f3 pipe_q2_f0 pipe_q2_f3 pipe_q3_f0 pipe_q3_f3 pipe_q1_f0; do
+for b in a_q4_base_f0 pipe_q4_f0 o_q4_base_f3 pipe_q4_f3 pipe_eg_q4_f3 eg_q4_f3_m4 eg_q4_f3_m3 pipe_q2_f0 pipe_q2_f3 pipe_eg_q2_f3 eg_q2_f3_m4 pipe_q3_f0 pipe_q3_f3 pipe_eg_q3_f3 pipe_q1_f0; do
   timeout 40 ./bin/$b 0 5 >> $O 2>&1 || echo "$b failed ($?)" >> $O
 done
 cat $O
