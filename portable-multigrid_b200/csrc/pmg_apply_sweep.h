@@ -493,7 +493,7 @@ struct PmgSweepTile {
           const double *Ac1 = (((P + c * P) & 1) ? Ae : Ao) + (P + c * P) * XPA;
 #pragma unroll
           for (int j = 0; j < N1; ++j) {
-            if (j > 0) vj = ((j & 1) ? Ac1 : Ac0)[j * XPA];
+            if (j > 0) vj = RL ? ((j & 1) ? Ac1 : Ac0)[j * XPA] : PMG_AROW(P + c * P + j);
             if (j == P && dir_hi && t.cy0 + c == p.ny - 1) vj = 0.0;
 #pragma unroll
             for (int kk = 0; kk < N1; ++kk) {
@@ -636,9 +636,9 @@ struct PmgSweepTile {
       const int ox = info & 0xFF, oy = (info >> 8) & 0xFF;
       const double *G = Cb + oy * XP + P + ox;
       const double *Mm = Db + oy * XP + P + ox;
-      const int64_t goff = glayer + (int64_t)oy * p.Nx + ox; // the column's dof in plane 0 of the layer
       double bbv[P], xov[P];
       if (EG && FULL && MODE != PMG_MODE_APPLY) { // direct epilogue inputs: issue the loads before the z-sweep arithmetic
+        const int64_t goff = glayer + (int64_t)oy * p.Nx + ox; // the column's dof in plane 0 of the layer
 #pragma unroll
         for (int k = 0; k < P; ++k) { bbv[k] = p.b[goff + k * plane]; xov[k] = has_xo ? p.xold[goff + k * plane] : 0.0; }
       }
@@ -658,7 +658,7 @@ struct PmgSweepTile {
       if (write) {
         const bool dirxy = (info >> 16) & 1;
         const int tbase = ((info >> 20) & 0xF) + T * ((info >> 24) & 0xF);
-        double *po = p.out + goff;
+        double *po = p.out + glayer + (int64_t)oy * p.Nx + ox;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
           const int gz = cz * P + k;
@@ -671,10 +671,10 @@ struct PmgSweepTile {
             const int fl = (q & 1) & t.plodd;
             double uc = 0.0, bb = 0.0, xo = 0.0, dinv = 1.0;
             if (MODE != PMG_MODE_APPLY || dir) uc = (q == 0) ? st.uP[ci] : Uc[(q - 1) * APLANE + (sa ^ fl)];
-            if (MODE != PMG_MODE_APPLY) bb = !EG ? Ec[q * EPLANE] : FULL ? bbv[k] : p.b[goff + k * plane];
-            if (has_xo) xo = !EG ? Ec[EBUF + q * EPLANE] : FULL ? xov[k] : p.xold[goff + k * plane];
+            if (MODE != PMG_MODE_APPLY) bb = !EG ? Ec[q * EPLANE] : FULL ? bbv[k] : p.b[(po - p.out) + k * plane];
+            if (has_xo) xo = !EG ? Ec[EBUF + q * EPLANE] : FULL ? xov[k] : p.xold[(po - p.out) + k * plane];
             if (MODE >= PMG_MODE_CHEB_FIRST) {
-              if (p.dinv_vec) dinv = p.dinv_vec[goff + k * plane];
+              if (p.dinv_vec) dinv = p.dinv_vec[glayer + (int64_t)oy * p.Nx + ox + k * plane];
               else if (FULL) dinv = st.dinv[ci][k];
               else dinv = p.dinv_tab[tbase + T * T * pmg_sweep_pos_type<P>(gz, p.Nz)];
             }
