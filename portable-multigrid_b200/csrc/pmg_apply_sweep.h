@@ -397,7 +397,22 @@ struct PmgSweepTile {
       bytes += issue_row(p.u, t.eA + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)yl * p.Nx, XPA, t.n_local,
                          A + k * APLANE + yl * XPA, bar);
     }
+#if defined(__CUDA_ARCH__) && defined(PMG_SWEEP_WARP_ARRIVE)
+    // experiment switch (tools/exp): one arrival per warp with the warp's byte count instead of one per thread
+    bytes = __reduce_add_sync(0xffffffffu, bytes);
+    if ((tid & 31) == 0) pmg_mbar_arrive_expect(bar, bytes);
+#else
     pmg_mbar_arrive_expect(bar, bytes);
+#endif
+  }
+  // arrivals a u-staging barrier expects per use: every staging thread, or every staging warp (PMG_SWEEP_WARP_ARRIVE)
+  static PMG_HD constexpr int stage_arrivals(int staging_threads)
+  {
+#if defined(PMG_SWEEP_WARP_ARRIVE)
+    return staging_threads / 32;
+#else
+    return staging_threads;
+#endif
   }
 
   // b (and x_old) rows of the owned columns of output planes gz0 .. gz0+npl-1 -> E with cp.async (LDGSTS), issued by the
@@ -787,7 +802,7 @@ struct PmgSweepTile {
     int n0 = cz_end - cz_first; if (n0 > LZ) n0 = LZ;
     ex.for_each_thread([&](int tid, ThreadState &) {
       if (tid == 0) {
-        for (int i = 0; i < NBAR; ++i) pmg_mbar_init(bars + i, NT);
+        for (int i = 0; i < NBAR; ++i) pmg_mbar_init(bars + i, stage_arrivals(NT));
         pmg_mbar_init_fence();
       }
     });

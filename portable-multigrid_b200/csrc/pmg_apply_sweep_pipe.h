@@ -58,7 +58,7 @@ struct PmgSweepPipe {
     int n0 = cz_end - cz_first; if (n0 > LZ) n0 = LZ;
     ex.for_each_thread([&](int tid, ThreadState &) {
       if (tid == 0) {
-        for (int i = 0; i < NBAR; ++i) pmg_mbar_init(bars + i, NG);
+        for (int i = 0; i < NBAR; ++i) pmg_mbar_init(bars + i, Base::stage_arrivals(NG));
         pmg_mbar_init_fence();
       }
     });

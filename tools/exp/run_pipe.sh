@@ -22,9 +22,14 @@ export EXP_SRC=exp_pipe.cu
   EXP_SRC=exp_sweep.cu ./build_exp.sh eg_q4_f3_m3 4 4 4 1 128 3 -DC_US=1 -DC_FM=3 -DC_EG=1
   EXP_SRC=exp_sweep.cu ./build_exp.sh o_q4_base_f3 4 4 4 1 128 3 -DC_US=1 -DC_FM=3
   EXP_SRC=exp_sweep.cu ./build_exp.sh a_q4_base_f0 4 4 4 1 128 3 -DC_US=1 -DC_FM=0
+  # the shipped Q4 apply (rolled loops, 4 CTAs/SM) without / with one mbarrier arrival per warp instead of per thread
+  EXP_SRC=exp_sweep.cu ./build_exp.sh c_q4_rl_m4_f0 4 4 4 1 128 4 -DC_US=1 -DC_FM=0 -DC_RL=1
+  EXP_SRC=exp_sweep.cu ./build_exp.sh wa_q4_rl_m4_f0 4 4 4 1 128 4 -DC_US=1 -DC_FM=0 -DC_RL=1 -DPMG_SWEEP_WARP_ARRIVE
+  EXP_SRC=exp_sweep.cu ./build_exp.sh wa_q4_f3 4 4 4 1 128 3 -DC_US=1 -DC_FM=3 -DPMG_SWEEP_WARP_ARRIVE
+  ./build_exp.sh pipe_wa_q4_f0 4 4 4 1 128 2 -DC_US=1 -DC_FM=0 -DC_RL=1 -DPMG_SWEEP_WARP_ARRIVE
 }
 O=../../gpurun_out/exp_pipe.txt
-for b in a_q4_base_f0 pipe_q4_f0 o_q4_base_f3 pipe_q4_f3 pipe_eg_q4_f3 eg_q4_f3_m4 eg_q4_f3_m3 pipe_q2_f0 pipe_q2_f3 pipe_eg_q2_f3 eg_q2_f3_m4 pipe_q3_f0 pipe_q3_f3 pipe_eg_q3_f3 pipe_q1_f0; do
+for b in a_q4_base_f0 c_q4_rl_m4_f0 wa_q4_rl_m4_f0 pipe_q4_f0 pipe_wa_q4_f0 wa_q4_f3 o_q4_base_f3 pipe_q4_f3 pipe_eg_q4_f3 eg_q4_f3_m4 eg_q4_f3_m3 pipe_q2_f0 pipe_q2_f3 pipe_eg_q2_f3 eg_q2_f3_m4 pipe_q3_f0 pipe_q3_f3 pipe_eg_q3_f3 pipe_q1_f0; do
   timeout 40 ./bin/$b 0 5 >> $O 2>&1 || echo "$b failed ($?)" >> $O
 done
 cat $O
