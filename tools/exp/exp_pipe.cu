@@ -72,7 +72,11 @@ __global__ void __launch_bounds__(RefTile::NT) ref_kern(const __grid_constant__ 
 __global__ void maxdiff(const double *a, const double *b, size_t n, double *res)
 {
   double m = 0.0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmax(m, fabs(a[i] - b[i]));
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double d = fabs(a[i] - b[i]);
+    if (!(d <= 1e300)) d = 1e300; // NaN (an unwritten or poisoned dof) counts as a mismatch, fmax would drop it
+    m = fmax(m, d);
+  }
   atomicMax((unsigned long long *)res, (unsigned long long)__double_as_longlong(m)); // non-negative doubles order like integers
 }
 __global__ void __launch_bounds__(Tile::NT, MINB) kern(const __grid_constant__ PmgSweepParams<PP> p)
