@@ -34,7 +34,7 @@ typedef struct pmgk_level {
   double Kref[PMGK_MAX_N1 * PMGK_MAX_N1]; /* 1-D cell stiffness matrix */
   const double *dinv_tab;  /* device, (p+2)^3 */
   const double *dinv_vec;  /* device, local vector or NULL */
-  int tile_variant;        /* tuning knob: 0 = default choice per level; 1 = line-marching kernel; 2, 3 = cell-tile kernel, small/large tiles; 4 = pipelined line-marching kernel (experimental) */
+  int tile_variant;        /* tuning knob: 0 = default choice per level; 1 = line-marching kernel; 2, 3 = cell-tile kernel, small/large tiles; 4, 5 = pipelined line-marching kernel (experimental; 5: fused modes without shared-memory boxes for b / x_old) */
   /* variable coefficient -div(a grad u) (BASELINE config 5; NULL = the reference's constant-coefficient operator):
      w_q a(x_q) on the lexicographic grid of all quadrature points, (nx n1) x (ny n1) x ((cz_hi - coef_cz0) n1), x fastest */
   const double *coef;

@@ -104,7 +104,7 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
 {
   const int64_t n_loc = (int64_t)lv->Nx * lv->Ny * lv->nzl;
   const bool sweep_kernel = lv->dim == 3 && !lv->coef &&
-                            (lv->tile_variant == 1 || lv->tile_variant == 4 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
+                            (lv->tile_variant == 1 || lv->tile_variant == 4 || lv->tile_variant == 5 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
   if (part != PMGK_PART_ALL && !sweep_kernel) return PMG_ERR_UNSUPPORTED; /* only the line-marching kernel launches in parts */
   if (lv->dim == 2) return pmg_dim2_apply(lv, mode, u, b, xold, out, f1, f2, s, geom);
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
@@ -113,11 +113,12 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
      kernel (direct loads, no staging prologue) for the small coarse levels, where launch-to-result latency is everything:
      measured on B200 (tools/small_levels.py) 5.6-7.2 us against 7.0-12.3 us per fused step for Q1 up to 32^3 cells and
      12.3 against 16.4 us for Q2 on 32^3; from 64^3 cells on the line-marching kernel wins (14.3 : 17.1, 38.9 : 55.3 us).
-     1 = line-marching always; 2, 3 = cell-tile always (small / large tiles); 4 = line-marching always, in its pipelined form
-     for degrees 1..5 (csrc/pmg_apply_sweep_pipe.h: experimental, not yet measured on the GPU). */
+     1 = line-marching always; 2, 3 = cell-tile always (small / large tiles); 4, 5 = line-marching always, in its pipelined form
+     for degrees 1..5 (csrc/pmg_apply_sweep_pipe.h: experimental, not yet measured on the GPU; 5 = b / x_old of the fused modes read
+     from global memory instead of shared-memory boxes). */
   const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
   const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
-  if (lv->tile_variant == 1 || lv->tile_variant == 4 || (lv->tile_variant == 0 && !small_level)) {
+  if (lv->tile_variant == 1 || lv->tile_variant == 4 || lv->tile_variant == 5 || (lv->tile_variant == 0 && !small_level)) {
     switch (mode) { /* one kernel per epilogue mode: csrc/pmg_apply_sweep_m<mode>.cu */
       case PMGK_APPLY: return pmg_sweep_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom, part);
       case PMGK_RESIDUAL: return pmg_sweep_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom, part);

@@ -34,11 +34,11 @@ pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, i
 }
 
 // the pipelined variant (csrc/pmg_apply_sweep_pipe.h, opt-in: PMG_TILE_VARIANT=4): two groups of NG threads per CTA
-template <int P, int BX, int BY, int LZ, int NG, int MINB, int US, int FM, int RL>
+template <int P, int BX, int BY, int LZ, int NG, int MINB, int US, int FM, int RL, int EG>
 __global__ void __launch_bounds__(2 * NG, MINB)
 pmg_sweep_pipe_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
-  using Tile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL>;
+  using Tile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL, EG>;
   extern __shared__ __align__(128) double pmg_sweep_smem[];
   PmgSweepDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -74,13 +74,13 @@ void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int min_c
 template <int P, int FM> struct PmgSweepModeTune { static constexpr int roll = 0, min_ctas = 0; };
 template <> struct PmgSweepModeTune<4, PMG_MODE_APPLY> { static constexpr int roll = 1, min_ctas = 4; };
 
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL, bool PIPE = false>
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL, bool PIPE = false, int EG = 0>
 int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1,
                  double f2, cudaStream_t stream, int *geom, int part)
 {
-  using Tile = std::conditional_t<PIPE, PmgSweepPipe<P, BX, BY, LZ, NT, US, FM, RL>, PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>>;
+  using Tile = std::conditional_t<PIPE, PmgSweepPipe<P, BX, BY, LZ, NT, US, FM, RL, EG>, PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>>;
   void (*kernel)(const PmgSweepParams<P>, int, int);
-  if constexpr (PIPE) kernel = pmg_sweep_pipe_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>;
+  if constexpr (PIPE) kernel = pmg_sweep_pipe_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL, EG>;
   else kernel = pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
@@ -126,15 +126,15 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
 }
 
 // the pipelined variant with the same tile, NG = the table's thread count per group; CTAs per SM as shared memory allows
-template <int P, int BX, int BY, int LZ, int NG, int US, int FM>
+template <int P, int BX, int BY, int LZ, int NG, int US, int FM, int EG>
 int launch_sweep_pipe(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                       cudaStream_t stream, int *geom, int part)
 {
   if constexpr (P <= 5) {
     constexpr int RL = (P >= 4); // rolled cell loops: the two groups' register budgets add up
-    using PipeTile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL>;
+    using PipeTile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL, EG>;
     constexpr int minb = (PipeTile::smem_doubles(FM != PMG_MODE_APPLY) * 8 + 1024 <= 113 * 1024) ? 2 : 1;
-    return launch_sweep<P, BX, BY, LZ, NG, minb, US, FM, RL, true>(lv, u, b, xold, out, f1, f2, stream, geom, part);
+    return launch_sweep<P, BX, BY, LZ, NG, minb, US, FM, RL, true, EG>(lv, u, b, xold, out, f1, f2, stream, geom, part);
   } else {
     return PMG_ERR_UNSUPPORTED;
   }
@@ -148,10 +148,15 @@ int launch_sweep_pipe(const pmgk_level *lv, const double *u, const double *b, co
 int PMG_SWEEP_CAT(pmg_sweep_dispatch_m, PMG_SWEEP_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
                                                            double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
-  if (lv->tile_variant == 4) { /* opt-in: the pipelined variant; degrees 1..5 (above, its buffers do not fit shared memory) */
+  if (lv->tile_variant == 4 || lv->tile_variant == 5) {
+    /* opt-in: the pipelined variant; degrees 1..5 (above, its buffers do not fit shared memory); 5 = with b / x_old read from
+       global memory by the z sweep (EG = 1; the same kernel as 4 for the plain apply) */
+    constexpr int eg = (PMG_SWEEP_TU_MODE != PMG_MODE_APPLY);
     switch (lv->degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
-  case P: if (P <= 5) return launch_sweep_pipe<P, BX, BY, LZ, NT, US, PMG_SWEEP_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom, part); break;
+  case P: if (P <= 5) return lv->tile_variant == 5 ? launch_sweep_pipe<P, BX, BY, LZ, NT, US, PMG_SWEEP_TU_MODE, eg>(lv, u, b, xold, out, f1, f2, s, geom, part) \
+                                                     : launch_sweep_pipe<P, BX, BY, LZ, NT, US, PMG_SWEEP_TU_MODE, 0>(lv, u, b, xold, out, f1, f2, s, geom, part); \
+    break;
 #include "pmg_apply_sweep_tiles.inc"
 #undef PMG_SWEEP_CASE
       default: break;
