@@ -103,10 +103,10 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
     configured = 1;
   }
   const int slots = pmgk_device_sm_count() * ctas_per_sm;
-  // a slab with neighbours gets at least three chunks, so that the launch can be split into the chunks that read ghost planes
-  // (first and last) and the others, which run while the ghost planes are in flight (host/pmg_operator.c)
-  const bool slab = (lv->cz_lo > 0 || lv->cz_hi < lv->nz);
-  choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, slab ? 3 : 1, &p.n_chunks, &p.layers_per_chunk);
+  // a launch in parts (PMG_HALO_OVERLAP=1, host/pmg_operator.c) needs at least three chunks: the first and the last read the
+  // slab's ghost planes, the others run while those are in flight.  A whole launch takes the cheapest chunking (thin slabs:
+  // 16 layers of 32 x 32 tiles at 8 GPUs cost 7 waves x 7.25 layers in three chunks, 5 x 9.25 in two)
+  choose_sweep_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, part != PMGK_PART_ALL ? 3 : 1, &p.n_chunks, &p.layers_per_chunk);
   pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
   p.mode = FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;

@@ -201,10 +201,12 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
     for lo, hi in splits:
         z0, nzl, _, _, zol, zoh = sl = slab_of(p, n, lo, hi)
         ul = u[z0 * plane:(z0 + nzl) * plane].copy()
-        ol = emu_apply(emu, p, n, ul, slab=sl, chunks=2, kernel=kernel)
-        owned = np.zeros(nzl * plane, bool)
-        owned[(zol - z0) * plane:(zoh - z0) * plane] = True
-        assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()
+        for chunks in (1, 2):  # a slab launched whole takes whatever chunking fills the SMs, one chunk included
+            ol = emu_apply(emu, p, n, ul, slab=sl, chunks=chunks, kernel=kernel)
+            owned = np.zeros(nzl * plane, bool)
+            owned[(zol - z0) * plane:(zoh - z0) * plane] = True
+            assert np.isnan(ol[~owned]).all() and not np.isnan(ol[owned]).any()
+            assert rel_l2(ol[owned], ref[zol * plane:zoh * plane]) < 1e-13
         got[zol * plane:zoh * plane] = ol[owned]
     assert rel_l2(got, ref) < 1e-13
 
