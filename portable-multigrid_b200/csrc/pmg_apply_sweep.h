@@ -376,10 +376,22 @@ struct PmgSweepTile {
         if (k >= npl) break;
         int64_t e = t.eA + (int64_t)(gz0 + k - p.z0) * plane + (int64_t)y0 * p.Nx; // element index of the row's xl = 0
         double *dst = A + k * APLANE + y0 * XPA + xl;
+#if defined(PMG_SWEEP_LEAN_LOADER)
+        // experiment switch (tools/exp): the shift of a row equals that of the row two below it (2 Nx is even), so it and the
+        // two pointers leave the row loop
+        const double *src = p.u + e + xl;
+        const int64_t sstep = 2 * (int64_t)p.Nx;
+        dst += shift_of(e);
+        for (int yl = y0; yl <= yl_hi; yl += 2) {
+          pmg_sweep_cp_async8(dst, src);
+          src += sstep; dst += 2 * XPA;
+        }
+#else
         for (int yl = y0; yl <= yl_hi; yl += 2) {
           pmg_sweep_cp_async8(dst + shift_of(e), p.u + e + xl);
           e += 2 * (int64_t)p.Nx; dst += 2 * XPA;
         }
+#endif
       }
     }
   }
