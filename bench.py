@@ -380,6 +380,25 @@ def main():
                 "hbm_copy_gbs_here": mb["hbm_copy_gbs"],
                 "note": "executed flops of owned DoFs (7 sweeps + epilogue); halo recompute not counted"}
 
+    # BASELINE configs[2] point of this degree (standalone apply on a ~100 M-DoF cube, SURVEY 8 "C3"): the same operator call on
+    # n = round(464 / p) cells per direction.  Last GPU work of the run and never a dependency of the line above.
+    apply_c3 = None
+    if world == 1 and args.config == "c2" and not coefficient:
+        try:
+            n3 = int(round(464.0 / p))
+            big = G.LaplaceOperator(ctx, p, n3)
+            ub, zb = big.initialize_dof_vector(), big.initialize_dof_vector()
+            ub.set(1.0)
+            for _ in range(3):
+                big.vmult(zb, ub)
+            ms_big = timed(lambda: big.vmult(zb, ub), 10)
+            nb = int(big.m())
+            apply_c3 = {"degree": p, "cells_per_dir": n3, "n_dofs": nb, "ms": ms_big, "gdofs": nb / (ms_big * 1e-3) / 1e9,
+                        "hbm_frac": 16.0 * nb / (ms_big * 1e-3) / 1e9 / peak}
+            del ub, zb, big
+        except Exception as e:
+            apply_c3 = {"error": repr(e)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -387,6 +406,7 @@ def main():
                    "parallelism": "z-slabs x%d" % world, "cuda_graph": True},
         "apply_gdofs": n_dofs / (ms_apply * 1e-3) / 1e9, "apply_ms": ms_apply,
         "apply_hbm_frac": 16.0 * n_local / (ms_apply * 1e-3) / 1e9 / peak,
+        "apply_c3": apply_c3,
         "cg_solve": cg,
         "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
         "clocks": clocks,
