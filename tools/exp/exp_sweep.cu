@@ -87,14 +87,21 @@ int main(int argc, char **argv)
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Tile::NT, smem));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-  if (chunks <= 0) { // waves * (layers + 1 + 1/P) minimal
-    const int slots = 148 * per_sm, tiles = p.tiles_x * p.tiles_y; double best = -1;
-    for (int c = 1; c <= n; ++c) { int lpc = (n + c - 1) / c; if ((n + lpc - 1) / lpc != c) continue;
-      long waves = ((long)tiles * c + slots - 1) / slots; double cost = waves * (lpc + (c > 1 ? 1.0 + 1.0 / P : 0.0));
-      if (best < 0 || cost < best) { best = cost; chunks = c; } }
-  }
-  p.layers_per_chunk = (n + chunks - 1) / chunks; p.n_chunks = (n + p.layers_per_chunk - 1) / p.layers_per_chunk;
-  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  const int chunks_arg = chunks;
+  // z-chunks: waves * (layers + 1 + 1/P) minimal for the CTA slots of the launch at hand (chosen per mode: the modes differ in
+  // shared memory, hence in resident CTAs per SM)
+  auto choose_chunks = [&](int per_sm_now) {
+    int c_best = chunks_arg;
+    if (c_best <= 0) {
+      const int slots = 148 * per_sm_now, tiles = p.tiles_x * p.tiles_y; double best = -1;
+      for (int c = 1; c <= n; ++c) { int lpc = (n + c - 1) / c; if ((n + lpc - 1) / lpc != c) continue;
+        long waves = ((long)tiles * c + slots - 1) / slots; double cost = waves * (lpc + (c > 1 ? 1.0 + 1.0 / P : 0.0));
+        if (best < 0 || cost < best) { best = cost; c_best = c; } }
+    }
+    p.layers_per_chunk = (n + c_best - 1) / c_best; p.n_chunks = (n + p.layers_per_chunk - 1) / p.layers_per_chunk;
+    return p.tiles_x * p.tiles_y * p.n_chunks;
+  };
+  int grid = choose_chunks(per_sm);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 #if C_FM >= 0
   for (int mode : {C_FM}) {
@@ -104,6 +111,7 @@ int main(int argc, char **argv)
     p.mode = mode; p.out = (mode == 3) ? xo : out;
     smem = Tile::smem_doubles(mode != 0) * 8;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Tile::NT, smem));
+    grid = choose_chunks(per_sm);
     for (int i = 0; i < 3; ++i) kern<<<grid, Tile::NT, smem>>>(p);
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
