@@ -1,0 +1,114 @@
+// pmg_apply_plane_launch.h -- kernel entry + launcher of the plane-per-step apply kernel (csrc/pmg_apply_plane.h) for ONE
+// epilogue mode.  Included by pmg_apply_plane_m{0..4}.cu, each of which defines PMG_PLANE_TU_MODE (0..3 = PmgApplyMode,
+// 4 = PMG_MODE_CHEB_STEP without x_old) and so provides pmg_plane_dispatch_m<mode>(); the translation units compile in parallel.
+#include "pmg_apply_plane.h"
+#include "pmg_cuda_common.h"
+#include "pmg_kernels.h"
+
+namespace {
+
+template <class Tile>
+struct PmgPlaneDeviceExec {
+  typename Tile::ThreadState st;
+  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM>
+__global__ void __launch_bounds__(NT, MINB)
+pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p)
+{
+  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ>;
+  extern __shared__ __align__(128) double pmg_plane_smem[];
+  PmgPlaneDeviceExec<Tile> ex;
+  const int b = blockIdx.x;
+  const int tile_x = b % p.tiles_x;
+  const int tile_y = (b / p.tiles_x) % p.tiles_y;
+  const int chunk = b / (p.tiles_x * p.tiles_y);
+  Tile::run(p, ex, pmg_plane_smem, tile_x, tile_y, chunk);
+}
+
+// z-chunks of a launch.  Measured on B200 (profiles/r02_plane_chunk_sweep.txt, Q4): one wave of CTAs that each march the
+// whole column is the SLOWEST choice at 100 M DoFs (96 GDoF/s against 130 with 8 chunks per tile; a random start delay per CTA
+// changes nothing, so it is not the lockstep of the phases -- the u-read and the out-write streams of all CTAs then sit a fixed
+// few planes apart in memory); about eight CTAs per slot on staggered z ranges is where the curve is flat.  A chunk costs
+// P + 2 steps on top of its own (the recomputed layer below it, fill and drain), so chunks keep >= ~32 steps -- unless that
+// leaves SMs without a CTA (mid-size levels), where filling the machine comes first.
+inline void choose_plane_chunks(int tiles, int layers, int slots, int degree, int *n_chunks, int *layers_per_chunk)
+{
+  const long c_target = (8L * slots + tiles - 1) / tiles;
+  const long c_fill = (slots + tiles - 1) / tiles;
+  const int lpc_min = (32 + degree - 1) / degree;
+  long c_cap = layers / lpc_min;
+  long c_fill_cap = layers / 2;
+  if (c_cap < 1) c_cap = 1;
+  if (c_fill_cap < 1) c_fill_cap = 1;
+  long c_floor = c_fill < c_fill_cap ? c_fill : c_fill_cap; // chunks needed to give every slot a CTA, at >= 2 layers each
+  if (c_floor < c_cap) c_floor = c_cap;
+  long c = c_target < c_floor ? c_target : c_floor;
+  if (c < 1) c = 1;
+  const int lpc = (layers + (int)c - 1) / (int)c;
+  *layers_per_chunk = lpc;
+  *n_chunks = (layers + lpc - 1) / lpc;
+}
+
+template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM>
+int launch_plane(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
+                 cudaStream_t stream, int *geom)
+{
+  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ>;
+  auto kernel = pmg_plane_kernel<P, BX, BY, NT, MINB, UZ, FM>;
+  PmgSweepParams<P> p;
+  p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
+  p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
+  p.faces = lv->faces;
+  p.z0 = lv->z0; p.nzl = lv->nzl;
+  p.cz_lo = lv->cz_lo; p.cz_hi = lv->cz_hi;
+  p.z_own_lo = lv->z_own_lo; p.z_own_hi = lv->z_own_hi;
+  p.tiles_x = Tile::tiles_of(lv->nx, lv->faces >> 1 & 1u, BX);
+  p.tiles_y = Tile::tiles_of(lv->ny, lv->faces >> 3 & 1u, BY);
+  const int smem_bytes = Tile::SMEM_DOUBLES * (int)sizeof(double);
+  // per device: the shared-memory opt-in and the occupancy belong to the device the launch goes to
+  enum { MAXDEV = 64 };
+  static int ctas_per_sm[MAXDEV];
+  int dev = 0;
+  PMG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAXDEV) return PMG_ERR_UNSUPPORTED;
+  int per_sm = __atomic_load_n(&ctas_per_sm[dev], __ATOMIC_ACQUIRE);
+  if (per_sm == 0) {
+    PMG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem_bytes));
+    if (per_sm < 1) return PMG_ERR_CUDA;
+    __atomic_store_n(&ctas_per_sm[dev], per_sm, __ATOMIC_RELEASE);
+  }
+  const int slots = pmgk_device_sm_count() * per_sm;
+  choose_plane_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, P, &p.n_chunks, &p.layers_per_chunk);
+  pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
+  p.mode = (FM == 4) ? PMG_MODE_CHEB_STEP : FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
+  p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
+  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
+  /* the kernel indexes inside a dof plane with 32-bit element offsets (planes themselves are 64-bit offsets apart) */
+  if ((int64_t)lv->Nx * lv->Ny * 4 >= (int64_t)1 << 31) return PMG_ERR_UNSUPPORTED;
+  kernel<<<grid, NT, smem_bytes, stream>>>(p);
+  PMG_CUDA_CHECK(cudaGetLastError());
+  pmg_count_launch(1);
+  return 0;
+}
+
+} // namespace
+
+#define PMG_PLANE_CAT2(a, b) a##b
+#define PMG_PLANE_CAT(a, b) PMG_PLANE_CAT2(a, b)
+
+int PMG_PLANE_CAT(pmg_plane_dispatch_m, PMG_PLANE_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
+                                                           double *out, double f1, double f2, cudaStream_t s, int *geom)
+{
+  switch (lv->degree) {
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ) \
+  case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom);
+#include "pmg_apply_plane_tiles.inc"
+#undef PMG_PLANE_CASE
+    default: return PMG_ERR_UNSUPPORTED;
+  }
+}

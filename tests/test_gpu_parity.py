@@ -18,18 +18,19 @@ HISTORY_TOL = 1e-10
 
 # PMG_TEST_PIPE=1 adds the pipelined line-marching kernel (PMG_TILE_VARIANT=4 and 5, csrc/pmg_apply_sweep_pipe.h: experimental,
 # emulator-verified, first GPU run pending) to the kernels every test is run with
-_KERNELS = ["auto", "sweep", "celltile"] + (["pipe", "pipe_eg"] if os.environ.get("PMG_TEST_PIPE") == "1" else [])
+_KERNELS = ["auto", "plane", "sweep", "celltile"] + (["pipe", "pipe_eg"] if os.environ.get("PMG_TEST_PIPE") == "1" else [])
 
 
 @pytest.fixture(autouse=True, params=_KERNELS)
 def apply_kernel(request, monkeypatch):
-    """Every test runs with the library's default choice of apply kernel (line-marching kernel for large levels, cell-tile
-    kernel for small ones) and with each of the two forced: the meshes here are small, so the default alone would never
-    reach the line-marching kernel.  PMG_TILE_VARIANT is read when an operator is created."""
+    """Every test runs with the library's default choice of apply kernel (plane-per-step kernel for large levels, cell-tile
+    kernel for small ones) and with each kernel forced: the meshes here are small, so the default alone would never reach the
+    large-level kernels ("plane": csrc/pmg_apply_plane.h, degrees 1..6, above that the line-marching kernel; "sweep": the
+    line-marching kernel of round 1, still used for degrees 7, 8).  PMG_TILE_VARIANT is read when an operator is created."""
     if request.param == "auto":
         monkeypatch.delenv("PMG_TILE_VARIANT", raising=False)
     else:
-        monkeypatch.setenv("PMG_TILE_VARIANT", {"sweep": "1", "celltile": "2", "pipe": "4", "pipe_eg": "5"}[request.param])
+        monkeypatch.setenv("PMG_TILE_VARIANT", {"sweep": "1", "celltile": "2", "pipe": "4", "pipe_eg": "5", "plane": "6"}[request.param])
     return request.param
 
 

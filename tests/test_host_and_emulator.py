@@ -107,7 +107,7 @@ def test_partition(pmg):
     assert pmg.host_partition(7, 1, 0) == (0, 7, True)
 
 
-KERNELS = ["sweep", "celltile"]
+KERNELS = ["sweep", "celltile", "plane"]
 
 
 # ---- the CUDA tile programs under the host emulator --------------------------------------------------
@@ -130,10 +130,10 @@ def emu_apply(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, 
     z0, nzl, czlo, czhi, zol, zoh = (0, Nz, 0, nz, 0, Nz) if slab is None else slab
     if out is None:
         out = np.full(u.shape, np.nan)
-    if kernel == "sweep":
+    if kernel in ("sweep", "plane"):
         M, K = np.zeros((p + 1) ** 2), np.zeros((p + 1) ** 2)
         emu.pmg_fe_pencil(C.c_int(p), P(M), P(K))
-        rc = emu.emu_sweep(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(M), P(K), P(h), mode,
+        rc = (emu.emu_sweep if kernel == "sweep" else emu.emu_plane)(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(M), P(K), P(h), mode,
                            P(u), P(b), P(xold), P(out), C.c_double(f1), C.c_double(f2), P(dinv_vec), P(tab))
     else:
         rc = emu.emu_apply(p, small, nx, ny, nz, C.c_uint(faces), z0, nzl, czlo, czhi, zol, zoh, chunks, P(S), P(lam), P(h), mode,
@@ -154,6 +154,8 @@ def slab_of(p, n, cz_lo, cz_hi):
 @pytest.mark.parametrize("small,chunks", [(1, 1), (1, 3), (0, 2)])
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_emulated_apply_matches_oracle(p, small, chunks, kernel, emu, oracle):
+    if kernel == "plane" and small == 0 and p > 6:
+        pytest.skip("the plane-per-step kernel ships tiles for degrees 1..6 (csrc/pmg_apply_plane_tiles.inc)")
     n = (5, 4, 3) if p < 5 else (3, 2, 3)
     mf = oracle.MatrixFree(3, p, n)
     u = splitmix_src(mf.n_dofs, salt=p)
@@ -209,6 +211,23 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
             assert rel_l2(ol[owned], ref[zol * plane:zoh * plane]) < 1e-13
         got[zol * plane:zoh * plane] = ol[owned]
     assert rel_l2(got, ref) < 1e-13
+
+
+@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("small,chunks", [(2, 2), (3, 1), (3, 3)])
+def test_emulated_plane_kernel_variants(p, small, chunks, emu, oracle):
+    """Plane-per-step kernel (csrc/pmg_apply_plane.h): threads of a phase run in descending order (small = 2: a hazard between
+    threads of one phase would show), the steps of a cell layer rolled (small = 3); mixed Dirichlet faces, fused step."""
+    n = (5, 3, 4) if p < 5 else (3, 2, 3)
+    for faces in (0x3F, 0x19):
+        mf = oracle.MatrixFree(3, p, n, faces=faces)
+        u, b, xo = (splitmix_src(mf.n_dofs, salt=s + p) for s in (1, 2, 3))
+        Au, dinv = mf.vmult(u), mf.compute_diagonal()
+        out = emu_apply(emu, p, n, u, small=small, chunks=chunks, faces=faces, kernel="plane")
+        assert not np.isnan(out).any()
+        assert rel_l2(out, Au) < 1e-13
+        ref = u + 0.3 * (u - xo) + 0.9 * dinv * (b - Au)
+        assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.9, small=small, chunks=chunks, faces=faces, kernel="plane"), ref) < 1e-13
 
 
 @pytest.mark.parametrize("p", range(1, 9))
