@@ -9,7 +9,8 @@ HBM.  `e2e` = the same through the C-ABI's host-buffer entry (pmg_vcycle_vmult_h
 from pinned memory, V-cycle, D2H of the correction).  `roofline` = the dominant kernel (the fused
 Chebyshev step on the finest level) timed alone with CUDA events on the library's stream.
 `--impl reference` times the reference's CPU algorithm (the oracle port: the reference itself cannot be
-compiled here) on the host cores for the same metric, on a bounded sample of the workload.
+compiled here) on the host cores for the same metric and the same workload (the configuration's one-GPU mesh; the sample
+is bounded by the number of cycles: <= 1 warm-up + <= 2 timed).
 """
 import argparse
 import json
@@ -27,7 +28,6 @@ METRIC = "GDoF/s of one multigrid V-cycle (fine-level DoFs / time); operator-app
 UNIT = "GDoF/s"
 DEGREE = 4
 CELLS = 64
-CPU_SAMPLE_CELLS = 16
 
 
 def scaled_cells(n, world):
@@ -140,15 +140,18 @@ def measured_peaks():
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v5_cheb_step_q4_c2.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_cheb_step_q4_c2.json")) as f:
             return json.load(f).get("dram_bytes_per_launch")
     except Exception:
         return None
 
 
-def run_reference(args):
-    """CPU arm: the oracle's V-cycle (port of the reference algorithm in the reference's data layout) on all
-    host threads, bounded sample: same hierarchy shape at CPU_SAMPLE_CELLS^3 cells."""
+def run_reference(args, cfg):
+    """CPU arm: the oracle's V-cycle (port of the reference algorithm in the reference's data layout) on all host threads,
+    on the SAME workload as the product arm at one GPU -- the configuration's own mesh and hierarchy (64^3 cells Q4 for c2:
+    3.7 GB of stored indices / Jacobians, ~10-20 s per V-cycle); the sample is bounded by the number of cycles (<= 1 warm-up,
+    <= 2 timed).  Under torchrun the product arm weak-scales the mesh; this arm keeps the one-GPU mesh (the CPU's throughput
+    does not depend on the size beyond its caches) and `config.workload` names what it ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,9 +159,7 @@ def run_reference(args):
     if "LOCAL_RANK" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import pyoracle as O
-    from helpers import splitmix_src
 
     try:
         O.build(native=True)
@@ -166,45 +167,50 @@ def run_reference(args):
         kind = "port (-march=native)"
     except Exception:
         kind = "port"
-    res = cpu_vcycle(O, args.steps, args.warmup)
-    name, _ = workload_name(DEGREE, (CELLS,) * 3, 1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    res = cpu_vcycle(O, cfg, steps=min(max(args.steps, 1), 2), warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "timing": "host wall clock around the oracle's V-cycle"},
+        "config": {"workload": res["workload"], "timing": "host wall clock around the oracle's V-cycle",
+                   "note": None if world == 1 else "the product arm runs this mesh per GPU, weak-scaled over %d GPUs" % world},
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"], "build": kind},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "apply_gdofs": res["apply_gdofs"],
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def cpu_vcycle(O, steps, warmup):
-    import numpy as np
+def cpu_vcycle(O, cfg, steps, warmup):
+    """The oracle's V-cycle on the configuration's one-GPU mesh: `warmup` untimed + `steps` timed cycles."""
     from helpers import splitmix_src
 
-    levels = hp_levels(DEGREE, (CPU_SAMPLE_CELLS,) * 3)
-    mfs = [O.MatrixFree(3, p, c) for (p, c) in levels]
+    p, cells = cfg["degree"], (cfg["cells"],) * 3
+    coef = cfg.get("coefficient", 0)
+    levels = hp_levels(p, cells) if cfg["hierarchy"] == "hp" else h_levels(p, cells)
+    mfs = [O.MatrixFree(3, d, c, coef=("c5" if coef else None)) for (d, c) in levels]
     trs = [O.Transfer(mfs[l - 1], mfs[l], "h" if levels[l][0] == levels[l - 1][0] else "p") for l in range(1, len(levels))]
-    vc = O.VCycle(mfs, trs)
+    vc = O.VCycle(mfs, trs, degree=cfg["cheb_degree"])
     vc.estimate()
     n = mfs[-1].n_dofs
     r = splitmix_src(n, mfs[-1].constrained())
-    for _ in range(max(1, min(warmup, 2))):
+    for _ in range(warmup):
         vc.vmult(r)
-    k = max(1, min(steps, 5))
     t0 = time.perf_counter()
-    for _ in range(k):
+    for _ in range(steps):
         vc.vmult(r)
-    dt = (time.perf_counter() - t0) / k
+    dt = (time.perf_counter() - t0) / steps
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(2):
         mfs[-1].vmult(r)
-    dta = (time.perf_counter() - t0) / 3
+    dta = (time.perf_counter() - t0) / 2
+    name, _ = workload_name(p, cells, 1, cfg["hierarchy"], cfg["cheb_degree"], coef)
     return {"value": n / dt / 1e9, "ms_per_step": dt * 1e3, "cores": O.num_threads(), "apply_gdofs": n / dta / 1e9,
-            "sample": "same hierarchy at %d^3 cells (%d DoFs), %d V-cycles; reference data layout "
-                      "(stored indices, masks, per-q-point Jacobians)" % (CPU_SAMPLE_CELLS, n, k)}
+            "steps": steps, "warmup": warmup, "workload": name,
+            "sample": "the full workload (%d DoFs), %d warm-up + %d timed V-cycles; reference data layout "
+                      "(stored indices, masks, per-q-point Jacobians)" % (n, warmup, steps)}
 
 
 def main():
@@ -224,7 +230,7 @@ def main():
     if args.cells is not None:
         cfg["cells"] = args.cells
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, cfg)
 
     import numpy as np
     import torch
@@ -410,7 +416,7 @@ def main():
         "cg_solve": cg,
         "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
         "clocks": clocks,
-        "roofline": {"kernel": ("pmg_var_kernel<%d>" if coefficient else "pmg_sweep_kernel<%d>") % p + " (fused Chebyshev step, finest level)",
+        "roofline": {"kernel": ("pmg_var_kernel<%d>" if coefficient else "pmg_plane_kernel<%d>" if p <= 6 else "pmg_sweep_kernel<%d>") % p + " (fused Chebyshev step, finest level)",
                      "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic() if args.config == "c2" and world == 1 else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_dof": bytes_per_dof, "ms_per_launch": ms_step, "fp64": fp64},
@@ -425,7 +431,7 @@ def main():
                 O.use_native()
             except Exception:
                 pass
-            res = cpu_vcycle(O, 3, 1)
+            res = cpu_vcycle(O, cfg, steps=1, warmup=1)
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"],
                                     "apply_gdofs": res["apply_gdofs"]}
         except Exception as e:  # the baseline is a reported number, never a dependency of the product path

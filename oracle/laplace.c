@@ -34,22 +34,24 @@ static void sweep(int dim, int n, int dir, const double *mat, int dof_to_quad, i
                   const double *in, double *out)
 {
   const int stride = (dir == 0) ? 1 : (dir == 1) ? n : n * n;
-  const int total = (dim == 3) ? n * n * n : n * n;
+  /* the n^(dim-1) lines along `dir`: their starts are o1 * s1 + o2 * s2 over the two other directions */
+  const int s1 = (dir == 0) ? n : 1, s2 = (dir == 2) ? n : n * n;
+  const int n2 = (dim == 3) ? n : 1;
   double line[ORC_MAX_DEGREE + 1];
-  for (int base = 0; base < total; ++base) {
-    /* enumerate line starts: index along dir is zero */
-    if ((base / stride) % n != 0) continue;
-    for (int b = 0; b < n; ++b) line[b] = in[base + b * stride];
-    for (int a = 0; a < n; ++a) {
-      double s = 0.0;
-      if (dof_to_quad)
-        for (int b = 0; b < n; ++b) s += mat[a * n + b] * line[b];
-      else
-        for (int b = 0; b < n; ++b) s += mat[b * n + a] * line[b];
-      if (add) out[base + a * stride] += s;
-      else out[base + a * stride] = s;
+  for (int o2 = 0; o2 < n2; ++o2)
+    for (int o1 = 0; o1 < n; ++o1) {
+      const int base = o1 * s1 + o2 * s2;
+      for (int b = 0; b < n; ++b) line[b] = in[base + b * stride];
+      for (int a = 0; a < n; ++a) {
+        double s = 0.0;
+        if (dof_to_quad)
+          for (int b = 0; b < n; ++b) s += mat[a * n + b] * line[b];
+        else
+          for (int b = 0; b < n; ++b) s += mat[b * n + a] * line[b];
+        if (add) out[base + a * stride] += s;
+        else out[base + a * stride] = s;
+      }
     }
-  }
 }
 
 void orc_cell_apply(const orc_mf *mf, int64_t cell, double *values, double *scratch)
