@@ -124,6 +124,18 @@ int pmg_vector_zero_out_ghost_values(pmg_vector *v);
 int pmg_vector_import_host(pmg_vector *v, const double *host_global);             /* ReadWriteVector import, H2D */
 int pmg_vector_export_host(const pmg_vector *v, double *host_global);             /* D2H; every rank receives the full vector */
 double *pmg_vector_device_ptr(pmg_vector *v);                                     /* get_values() */
+/* the rank's part (get_vector_partitioner analogue, include/base/portable_laplace_operator_base.h:58-59): stored dof planes
+   [z0, z0 + n_planes) of plane_size dofs, of which [z_own_lo, z_own_hi) are owned; lexicographic inside a plane */
+int pmg_vector_local_range(const pmg_vector *v, int64_t *plane_size, int *z0, int *n_planes, int *z_own_lo, int *z_own_hi);
+/* owned planes only <-> host (no collective; ghosts untouched).  import is stream-ordered: keep the buffer until pmg_context_sync */
+int pmg_vector_import_owned(pmg_vector *v, const double *host_owned);
+int pmg_vector_export_owned(const pmg_vector *v, double *host_owned);
+/* all stored planes, ghosts included <-> host (blocking) */
+int pmg_vector_import_local(pmg_vector *v, const double *host_local);
+int pmg_vector_export_local(const pmg_vector *v, double *host_local);
+/* a vector over caller-owned device memory laid out like `like` (all stored planes): the adapter wraps the storage of a
+   LinearAlgebra::distributed::Vector<double, MemorySpace::Default> instead of copying it per vmult; destroy frees the handle only */
+int pmg_vector_wrap(const pmg_vector *like, double *device_values, pmg_vector **out);
 
 /* ---- MGTransferBase (include/base/portable_mg_transfer_base.h:21-37) ---- */
 /* GeometricTransfer::reinit  include/multigrid/portable_geometric_transfer.h:892-1327 */
@@ -150,6 +162,8 @@ int pmg_vcycle_create(pmg_operator *const *ops, pmg_transfer *const *transfers, 
 int pmg_vcycle_destroy(pmg_vcycle *v);
 int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src);      /* :79-94 */
 /* HOST-buffer variant (fine-level m() doubles each): H2D src, V-cycle, D2H dst */
+/* the same with every rank's OWNED part of the vectors in host memory (plane_size * (z_own_hi - z_own_lo) doubles each) */
+int pmg_vcycle_vmult_host_owned(pmg_vcycle *v, double *dst_host_owned, const double *src_host_owned);
 int pmg_vcycle_vmult_host(pmg_vcycle *v, double *dst_host, const double *src_host);
 /* 1 = replay the cycle from a CUDA graph (default), 0 = launch kernel by kernel */
 int pmg_vcycle_set_graph(pmg_vcycle *v, int enable);

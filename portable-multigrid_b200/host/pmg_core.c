@@ -17,6 +17,7 @@
  */
 #include "pmg_internal.h"
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -228,8 +229,36 @@ int pmg_vector_destroy(pmg_vector *v)
 {
   if (!v) return PMG_OK;
   cudaStreamSynchronize(v->ctx->stream);
-  cudaFree(v->d);
+  if (!v->borrowed) cudaFree(v->d);
   free(v);
+  return PMG_OK;
+}
+
+/* A vector over device memory the caller owns (the reference adapter hands in the storage of a
+   LinearAlgebra::distributed::Vector<double, MemorySpace::Default>: no copy per vmult).  The array holds the rank's
+   stored planes -- pmg_vector_local_range() -- in lexicographic order; it must stay valid while the handle lives. */
+int pmg_vector_wrap(const pmg_vector *like, double *device_values, pmg_vector **out)
+{
+  if (!like || !device_values || !out) return PMG_ERR_ARG;
+  if (((uintptr_t)device_values & 15) != 0) { pmg_set_error("pmg_vector_wrap: the array is not 16-byte aligned"); return PMG_ERR_ARG; }
+  pmg_vector *v = (pmg_vector *)calloc(1, sizeof(*v));
+  if (!v) return PMG_ERR_NOMEM;
+  v->ctx = like->ctx; v->lay = like->lay; v->d = device_values; v->borrowed = 1;
+  *out = v;
+  return PMG_OK;
+}
+
+/* The rank's part of the vector (get_vector_partitioner analogue, include/base/portable_laplace_operator_base.h:58-59):
+   stored dof planes [z0, z0 + n_planes) of plane_size dofs each, of which [z_own_lo, z_own_hi) are owned, the others ghosts. */
+int pmg_vector_local_range(const pmg_vector *v, int64_t *plane_size, int *z0, int *n_planes, int *z_own_lo, int *z_own_hi)
+{
+  if (!v) return PMG_ERR_ARG;
+  const pmg_layout *l = &v->lay;
+  if (plane_size) *plane_size = l->plane;
+  if (z0) *z0 = l->active ? l->z0 : 0;
+  if (n_planes) *n_planes = l->active ? l->nzl : 0;
+  if (z_own_lo) *z_own_lo = l->active ? l->z_own_lo : 0;
+  if (z_own_hi) *z_own_hi = l->active ? l->z_own_hi : 0;
   return PMG_OK;
 }
 
@@ -410,6 +439,51 @@ int pmg_vector_compress_add(pmg_vector *v)
     PMG_CHECK(pmgk_axpby(dst, 1.0, dst, 1.0, from_lower, plane, ctx->stream));
   }
   PMG_CUDA(cudaFreeAsync(tmp, ctx->stream));
+  return PMG_OK;
+}
+
+/* ---- host import / export of the rank's own part: the owned planes only (ghost planes are not touched: an operator
+   application refreshes them); host_owned holds plane_size * (z_own_hi - z_own_lo) doubles.  No collective, no staging of the
+   global vector: this is what a distributed caller uses (pmg_vector_export_host assembles the GLOBAL vector on every rank). */
+int pmg_vector_import_owned(pmg_vector *v, const double *host_owned)
+{
+  if (!v || !host_owned) return PMG_ERR_ARG;
+  const pmg_layout *l = &v->lay;
+  if (!l->active) return PMG_OK;
+  const int64_t n = l->plane * (l->z_own_hi - l->z_own_lo);
+  PMG_CUDA(cudaMemcpyAsync(v->d + l->plane * (l->z_own_lo - l->z0), host_owned, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, v->ctx->stream));
+  return PMG_OK; /* stream-ordered: host_owned must stay unchanged until pmg_context_sync() or the next blocking call */
+}
+
+int pmg_vector_export_owned(const pmg_vector *v, double *host_owned)
+{
+  if (!v || !host_owned) return PMG_ERR_ARG;
+  const pmg_layout *l = &v->lay;
+  if (!l->active) return PMG_OK;
+  const int64_t n = l->plane * (l->z_own_hi - l->z_own_lo);
+  PMG_CUDA(cudaMemcpyAsync(host_owned, v->d + l->plane * (l->z_own_lo - l->z0), sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, v->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return PMG_OK;
+}
+
+/* every stored plane, ghosts included (tests of the ghost operations) */
+int pmg_vector_export_local(const pmg_vector *v, double *host_local)
+{
+  if (!v || !host_local) return PMG_ERR_ARG;
+  const pmg_layout *l = &v->lay;
+  if (!l->active) return PMG_OK;
+  PMG_CUDA(cudaMemcpyAsync(host_local, v->d, sizeof(double) * (size_t)l->n_local, cudaMemcpyDeviceToHost, v->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return PMG_OK;
+}
+
+int pmg_vector_import_local(pmg_vector *v, const double *host_local)
+{
+  if (!v || !host_local) return PMG_ERR_ARG;
+  const pmg_layout *l = &v->lay;
+  if (!l->active) return PMG_OK;
+  PMG_CUDA(cudaMemcpyAsync(v->d, host_local, sizeof(double) * (size_t)l->n_local, cudaMemcpyHostToDevice, v->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(v->ctx->stream));
   return PMG_OK;
 }
 

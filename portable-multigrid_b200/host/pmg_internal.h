@@ -88,6 +88,7 @@ struct pmg_vector {
   pmg_context *ctx;
   pmg_layout lay;
   double *d;
+  int borrowed; /* d belongs to the caller (pmg_vector_wrap): never freed here */
 };
 
 struct pmg_operator {

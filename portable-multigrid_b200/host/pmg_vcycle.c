@@ -259,6 +259,19 @@ int pmg_vcycle_vmult_host(pmg_vcycle *v, double *dst_host, const double *src_hos
   return pmg_vector_export_host(v->host_dst, dst_host);
 }
 
+int pmg_vcycle_vmult_host_owned(pmg_vcycle *v, double *dst_host_owned, const double *src_host_owned)
+{
+  if (!v || !dst_host_owned || !src_host_owned) return PMG_ERR_ARG;
+  const int top = v->n_levels - 1;
+  if (!v->host_dst) {
+    PMG_CHECK(pmg_vector_create_layout(v->ctx, &v->op[top]->lay, &v->host_dst));
+    PMG_CHECK(pmg_vector_create_layout(v->ctx, &v->op[top]->lay, &v->host_src));
+  }
+  PMG_CHECK(pmg_vector_import_owned(v->host_src, src_host_owned));
+  PMG_CHECK(pmg_vcycle_vmult(v, v->host_dst, v->host_src));
+  return pmg_vector_export_owned(v->host_dst, dst_host_owned);
+}
+
 int pmg_vcycle_profile(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src, double *out_ms, int cap_levels)
 {
   if (!v || !out_ms || cap_levels < v->n_levels) return PMG_ERR_ARG;

@@ -175,6 +175,40 @@ class Vector:
     def device_ptr(self):
         return lib().pmg_vector_device_ptr(self.h)
 
+    def local_range(self):
+        """(plane_size, z0, n_planes, z_own_lo, z_own_hi): the rank's stored / owned dof planes."""
+        pl = C.c_int64()
+        z0, nz, lo, hi = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _ck(lib().pmg_vector_local_range(self.h, C.byref(pl), C.byref(z0), C.byref(nz), C.byref(lo), C.byref(hi)))
+        return pl.value, z0.value, nz.value, lo.value, hi.value
+
+    def import_owned(self, a):
+        _ck(lib().pmg_vector_import_owned(self.h, _host_ptr(a)))
+        self.ctx.sync()
+
+    def export_owned(self, out=None):
+        pl, _, _, lo, hi = self.local_range()
+        if out is None:
+            out = np.empty(pl * (hi - lo))
+        _ck(lib().pmg_vector_export_owned(self.h, _host_ptr(out)))
+        return out
+
+    def import_local(self, a):
+        _ck(lib().pmg_vector_import_local(self.h, _host_ptr(a)))
+
+    def export_local(self, out=None):
+        pl, _, nz, _, _ = self.local_range()
+        if out is None:
+            out = np.empty(pl * nz)
+        _ck(lib().pmg_vector_export_local(self.h, _host_ptr(out)))
+        return out
+
+    def wrap(self, device_ptr):
+        """A non-owning vector with this vector's layout over caller-owned device memory (pmg_vector_wrap)."""
+        v = _vp()
+        _ck(lib().pmg_vector_wrap(self.h, C.c_void_p(device_ptr), C.byref(v)))
+        return Vector(v, self.ctx)
+
 
 class LaplaceOperator:
     """Portable::LaplaceOperator (reference include/operators/portable_laplace_operator.h:383-461)."""
@@ -335,6 +369,10 @@ class VCycleMultigrid:
 
     def vmult_host(self, dst, src):
         _ck(lib().pmg_vcycle_vmult_host(self.h, _host_ptr(dst), _host_ptr(src)))
+
+    def vmult_host_owned(self, dst, src):
+        """Every rank passes its OWNED part of the vectors (host memory)."""
+        _ck(lib().pmg_vcycle_vmult_host_owned(self.h, _host_ptr(dst), _host_ptr(src)))
 
     def set_graph(self, enable):
         _ck(lib().pmg_vcycle_set_graph(self.h, C.c_int(1 if enable else 0)))

@@ -258,6 +258,127 @@ def test_vcycle_and_cg_match_oracle(kind, p, n, pmg, ctx, oracle):
     assert abs(norm - 0.0249871331) < 2e-4  # analytic ||u||_L2 for -Laplace u = 1 on the unit cube
 
 
+# ---- the BASELINE.json configurations at their own size ("no oracle comparison at any BASELINE size").
+# These run once, with the library's own kernel choice (the large-level kernels, chunked multi-wave launches included).
+def _only_default_kernel(apply_kernel):
+    if apply_kernel != "auto":
+        pytest.skip("BASELINE-size comparison runs once, with the library's own kernel choice")
+
+
+def test_baseline_config1_full_size(pmg, ctx, oracle, apply_kernel):
+    """configs[0]: Q2, 64^3 cells (2 146 689 DoFs), geometric multigrid 64 -> 1 cells, V(2,2) Chebyshev(3)-Jacobi, CG to 1e-12:
+    operator apply <= 1e-12, V-cycle <= 1e-10, same CG iteration count, residual history within 1e-10."""
+    _only_default_kernel(apply_kernel)
+    levels = hierarchy_levels("h", 2, 64)
+    mfs, trs, vc_ref = _oracle_hierarchy(oracle, levels, degree=3)
+    ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels, degree=3)
+    top = ops[-1]
+    assert top.m() == mfs[-1].n_dofs == 2146689
+    src = splitmix_src(mfs[-1].n_dofs, salt=21)
+    s, d = top.vector_from(src), top.initialize_dof_vector()
+    top.vmult(d, s)
+    assert rel_l2(d.export_host(), mfs[-1].vmult(src)) <= APPLY_TOL
+    est = vc_ref.estimate()
+    for l, sm in enumerate(smoothers):
+        info = sm.info()
+        assert info["degree"] == est[l][2] and info["cg_iterations"] == est[l][3], (l, info, est[l])
+        assert abs(info["lambda_max"] - est[l][1]) <= 1e-8 * est[l][1]
+    r = splitmix_src(mfs[-1].n_dofs, mfs[-1].constrained(), salt=22)
+    z_ref = vc_ref.vmult(r)
+    dr, dz = top.vector_from(r), top.initialize_dof_vector()
+    for rep in range(3):  # eager, capture, replay
+        mg.vmult(dz, dr)
+        assert rel_l2(dz.export_host(), z_ref) <= HISTORY_TOL, rep
+    b_ref = mfs[-1].assemble_rhs()
+    b, x = top.initialize_dof_vector(), top.initialize_dof_vector()
+    top.assemble_rhs(b)
+    x_ref, it_ref, hist_ref, rc_ref = oracle.cg_solve(mfs[-1], b_ref, vc_ref)
+    it, hist, rc = pmg.cg_solve(top, x, b, mg)
+    assert rc == 0 and rc_ref == 0 and it == it_ref, (rc, rc_ref, it, it_ref)
+    assert np.all(np.abs(hist - hist_ref) <= HISTORY_TOL * hist_ref[0])
+    assert rel_l2(x.export_host(), x_ref) <= 1e-9
+
+
+def test_baseline_config2_hierarchy_32_cells(pmg, ctx, oracle, apply_kernel):
+    """configs[1]'s hierarchy (Q4 -> Q2 -> Q1 + geometric levels, Chebyshev(5)) at 32^3 cells (2 146 689 DoFs): apply, V-cycle
+    and the CG solve against the oracle."""
+    _only_default_kernel(apply_kernel)
+    levels = hierarchy_levels("hp", 4, 32)
+    mfs, trs, vc_ref = _oracle_hierarchy(oracle, levels)
+    ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)
+    top = ops[-1]
+    for l in (len(levels) - 1, len(levels) - 2):  # the Q4 and the Q2 level: large-level kernels
+        src = splitmix_src(mfs[l].n_dofs, salt=30 + l)
+        s, d = ops[l].vector_from(src), ops[l].initialize_dof_vector()
+        ops[l].vmult(d, s)
+        assert rel_l2(d.export_host(), mfs[l].vmult(src)) <= APPLY_TOL
+    vc_ref.estimate()
+    r = splitmix_src(mfs[-1].n_dofs, mfs[-1].constrained(), salt=23)
+    z_ref = vc_ref.vmult(r)
+    dr, dz = top.vector_from(r), top.initialize_dof_vector()
+    for rep in range(3):
+        mg.vmult(dz, dr)
+        assert rel_l2(dz.export_host(), z_ref) <= HISTORY_TOL, rep
+    b_ref = mfs[-1].assemble_rhs()
+    b, x = top.initialize_dof_vector(), top.initialize_dof_vector()
+    top.assemble_rhs(b)
+    x_ref, it_ref, hist_ref, rc_ref = oracle.cg_solve(mfs[-1], b_ref, vc_ref)
+    it, hist, rc = pmg.cg_solve(top, x, b, mg)
+    assert rc == 0 and rc_ref == 0 and it == it_ref, (rc, rc_ref, it, it_ref)
+    assert np.all(np.abs(hist - hist_ref) <= HISTORY_TOL * hist_ref[0])
+
+
+def test_baseline_config2_apply_and_step_full_size(pmg, ctx, oracle, apply_kernel):
+    """configs[1] at its own size: Q4, 64^3 cells (16 974 593 DoFs).  The operator apply and one fused Chebyshev step of the
+    finest level against the oracle (the oracle's cell loop in the reference layout: 3.7 GB, ~1 s per apply)."""
+    _only_default_kernel(apply_kernel)
+    mf = oracle.MatrixFree(3, 4, 64)
+    op = pmg.LaplaceOperator(ctx, 4, 64)
+    assert op.m() == mf.n_dofs == 16974593
+    src = splitmix_src(mf.n_dofs, salt=24)
+    Au = mf.vmult(src)
+    s, d = op.vector_from(src), op.initialize_dof_vector()
+    op.vmult(d, s)
+    assert rel_l2(d.export_host(), Au) <= APPLY_TOL
+    bb, xo = splitmix_src(mf.n_dofs, salt=25), splitmix_src(mf.n_dofs, salt=26)
+    db, dx = op.vector_from(bb), op.vector_from(xo)
+    op.chebyshev_step(dx, s, dx, db, 0.37, 0.81)  # x_old overwritten in place, as the smoother calls it
+    ref = src + 0.37 * (src - xo) + 0.81 * mf.compute_diagonal() * (bb - Au)
+    assert rel_l2(dx.export_host(), ref) <= APPLY_TOL
+
+
+def test_vector_local_part_wrap_and_ghost_operations_one_rank(pmg, ctx, oracle):
+    """The partitioner-style vector API on one rank: the local range is the whole vector, owned import / export round-trips,
+    a wrapped caller-owned array is used in place (no copy) and the ghost operations are no-ops (no ghosts exist)."""
+    p, n = 2, (5, 4, 6)
+    mf = oracle.MatrixFree(3, p, n)
+    op = pmg.LaplaceOperator(ctx, p, n)
+    src = splitmix_src(mf.n_dofs, salt=31)
+    v = op.initialize_dof_vector()
+    plane, z0, nz, lo, hi = v.local_range()
+    assert (plane, z0, nz, lo, hi) == (mf.nd[0] * mf.nd[1], 0, mf.nd[2], 0, mf.nd[2])
+    v.import_owned(src)
+    assert np.array_equal(v.export_owned(), src) and np.array_equal(v.export_local(), src) and np.array_equal(v.export_host(), src)
+    for f in (v.update_ghost_values, v.zero_out_ghost_values, v.compress_add):
+        f()
+        assert np.array_equal(v.export_host(), src)
+    # wrap: the operator reads and writes the caller's arrays (here: two library vectors' storage seen through new handles)
+    a, b = op.vector_from(src), op.initialize_dof_vector()
+    wa, wb = a.wrap(a.device_ptr()), b.wrap(b.device_ptr())
+    op.vmult(wb, wa)
+    assert rel_l2(b.export_host(), mf.vmult(src)) <= APPLY_TOL
+    del wa, wb  # frees the handles only
+    assert np.array_equal(a.export_host(), src)
+    # V-cycle through host buffers holding the owned part == through the global host buffers
+    levels = hierarchy_levels("h", 2, 8)
+    ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)
+    r = splitmix_src(ops[-1].m(), salt=32)
+    z1, z2 = np.empty_like(r), np.empty_like(r)
+    mg.vmult_host(z1, r)
+    mg.vmult_host_owned(z2, r)
+    assert np.array_equal(z1, z2)
+
+
 def test_vcycle_graph_vs_eager_bitwise(pmg, ctx):
     levels = hierarchy_levels("h", 2, 16)
     ops, transfers, smoothers, mg = pmg.build_hierarchy(ctx, levels)

@@ -45,6 +45,42 @@ def main():
         op.vmult(d, s)
         report("vmult p=%d n=%s" % (p, n), rel_l2(d.export_host(), mf.vmult(src)), 1e-12)
         report("dot p=%d" % p, abs(s.dot(s) - float(src @ src)) / float(src @ src), 1e-13)
+    # 1b. the rank's part of a vector and the ghost operations (LinearAlgebra::distributed::Vector update_ghost_values /
+    #     zero_out_ghost_values / compress(add)) on slabs
+    for p, n in [(2, (8, 6, 4 * world)), (3, (4, 4, 2 * world))]:  # > coarse threshold: distributed levels
+        mf = O.MatrixFree(3, p, n)
+        op = G.LaplaceOperator(ctx, p, n)
+        g = splitmix_src(mf.n_dofs, salt=40 + p)
+        v = op.initialize_dof_vector()
+        plane, z0, nzl, lo, hi = v.local_range()
+        tot = torch.tensor([hi - lo], device="cuda")
+        dist.all_reduce(tot)
+        report("owned planes tile the mesh p=%d" % p, float(abs(int(tot.item()) - mf.nd[2])), 0.0)
+        v.import_owned(g[lo * plane:hi * plane].copy())  # ghosts still zero
+        loc = v.export_local()
+        own = slice((lo - z0) * plane, (hi - z0) * plane)
+        ghost = np.ones(nzl * plane, bool)
+        ghost[own] = False
+        report("import_owned leaves ghosts p=%d" % p, float(np.abs(loc[ghost]).max() if ghost.any() else 0.0), 0.0)
+        report("export_owned round trip p=%d" % p, float(np.abs(v.export_owned() - g[lo * plane:hi * plane]).max()), 0.0)
+        v.update_ghost_values()
+        report("update_ghost_values p=%d" % p, float(np.abs(v.export_local() - g[z0 * plane:(z0 + nzl) * plane]).max()), 0.0)
+        report("export_host after update p=%d" % p, float(np.abs(v.export_host() - g).max()), 0.0)
+        v.zero_out_ghost_values()
+        loc = v.export_local()
+        report("zero_out_ghost_values p=%d" % p, float(np.abs(loc[ghost]).max() if ghost.any() else 0.0) + float(np.abs(loc[own] - g[lo * plane:hi * plane]).max()), 0.0)
+        # compress(add): every stored copy of a dof is summed into its owner.  All stored planes = 1 -> an owned plane ends up
+        # with 1 + the number of neighbours that store it as a ghost
+        v.import_local(np.ones(nzl * plane))
+        v.compress_add()
+        got = v.export_owned().reshape(hi - lo, plane)[:, 0]
+        cnt = np.ones(mf.nd[2])
+        ranges = [None] * world
+        dist.all_gather_object(ranges, (z0, nzl, lo, hi))
+        for (rz0, rn, rlo, rhi) in ranges:
+            for z in list(range(rz0, rlo)) + list(range(rhi, rz0 + rn)):
+                cnt[z] += 1
+        report("compress_add p=%d" % p, float(np.abs(got - cnt[lo:hi]).max()), 0.0)
     # 2. transfers between two distributed levels, and between a distributed and a gathered level
     for kind, pc, pf, nc in [("h", 2, 2, (3, 2, 2 * world)), ("p", 1, 3, (3, 4, 2 * world)), ("h", 1, 1, (4, 4, world))]:
         nf = tuple(2 * c for c in nc) if kind == "h" else nc
