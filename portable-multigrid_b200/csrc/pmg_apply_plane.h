@@ -145,7 +145,8 @@ struct PmgPlaneTile {
 
   struct ThreadState {
     double acc[IX][P][N1]; // z sweep: sums of the current layer's planes r = 0..P for node i of the item's cell row
-    int ld_off;            // loader: element offset of (row tid / LW, column tid % LW) inside a dof plane
+    const double *ld_src;  // loader: the thread's first element (row tid / LW, column tid % LW) of the next plane to fetch
+    int ld_off;            // its element offset inside a dof plane
     int ld_dst;            // its byte offset in shared memory (ring slot 0)
     unsigned ld_mask;      // bit k: element of row tid / LW + k LR is inside the mesh and not Dirichlet (else it stays 0)
     int yi[IY];            // y item: offset of its first u row in a u plane | -1
@@ -275,19 +276,19 @@ struct PmgPlaneTile {
   }
 
   // ---- loader: the u plane at `up` -> ring slot U, asynchronously (one commit group per plane, empty ones included) --------
-  static PMG_HD void load_plane(const PmgSweepParams<P> &p, const ThreadState &st, const double *up, double *smem, unsigned base32,
-                                int slot, bool doit)
+  static PMG_HD void load_plane(const PmgSweepParams<P> &p, ThreadState &st, int64_t plane, double *smem, unsigned base32, int slot, bool doit)
   {
     if (doit) {
-      // one destination address and one source pointer per thread, pinned; row k is a constant / a multiple of the row step away
+      // one destination address and one source pointer per thread; row k is a constant / a multiple of the row step away
       unsigned dst = base32 + (unsigned)st.ld_dst + (unsigned)(slot * UPLANE * 8);
-      const double *src = up + st.ld_off; // 32-bit element offsets: a local vector holds < 2^31 dofs (checked by the launcher)
-      PMG_KEEP(dst); PMG_OPAQUE_PTR(src);
-      const int rstep = LR * p.Nx;
+      PMG_KEEP(dst);
+      const double *src = st.ld_src;
+      const int rstep = LR * p.Nx; // 32-bit element offsets inside a plane (checked by the launcher)
 #pragma unroll
       for (int k = 0; k < NLD; ++k)
         if (st.ld_mask >> k & 1u) pmg_plane_cp_async8(smem, base32, dst - base32 + k * LR * UP * 8, src + k * rstep);
     }
+    st.ld_src += plane; // the plane after it, fetched or not
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 #endif
@@ -437,7 +438,7 @@ struct PmgPlaneTile {
   static PMG_HD void epi_issue_t(const PmgSweepParams<P> &p, const TileGeom &t, ThreadState &st, int gz, int64_t eoff)
   {
     constexpr int NA = n_arrays(MODE);
-    if (NA == 0 || gz < p.z_own_lo || gz >= p.z_own_hi) return;
+    if (NA == 0) return;
     constexpr bool has_xo = (MODE == PMG_MODE_CHEB_STEP);
     // per-thread pointers to the thread's first dof, pinned; row k is k row steps away
     const double *pb = p.b + eoff + st.e_off, *pu = p.u + eoff + st.e_off, *px = has_xo ? p.xold + eoff + st.e_off : nullptr;
@@ -516,7 +517,6 @@ struct PmgPlaneTile {
   static PMG_HD void epilogue_m(const PmgSweepParams<P> &p, const TileGeom &t, const ThreadState &st, const double *smem, int slot,
                                 int gz, int64_t eoff, int tid)
   {
-    if (gz < p.z_own_lo || gz >= p.z_own_hi) return; // (slabs: the recomputed layer's planes belong to the neighbour)
     if (t.dirxy || gz == t.zlo || gz == t.zhi) epilogue_t<MODE, true>(p, t, st, smem, slot, gz, eoff, tid);
     else epilogue_t<MODE, false>(p, t, st, smem, slot, gz, eoff, tid);
   }
@@ -541,9 +541,10 @@ struct PmgPlaneTile {
     int us;           // ring slot of the current plane
     int gz_last;      // last plane of the march (the chunk's top vertex plane)
     int gz_stop;      // last step of the march: the last output plane leaves there
+    int fetch_max;    // last plane that is fetched (the march's last plane, or the one below a Dirichlet top face)
+    int q_lo, q_hi;   // output planes of the chunk that this rank owns: [q_lo, q_hi)
+    int64_t eq;       // element offset of the tile's first owned dof in plane gz - P - 1 (the plane whose epilogue the step runs)
     unsigned base32;  // 32-bit shared-window address of the CTA's shared memory
-    int64_t eoff;     // element offset of the tile's first owned dof in the plane of the current step
-    const double *up; // the u plane of the current step
   };
   // The output plane whose epilogue runs in the step of plane index gz, and its place in the output box: plane q leaves P + 1
   // steps after its own step (a cell layer closes at the vertex step of the layer above, its planes leave one per step; the
@@ -554,7 +555,7 @@ struct PmgPlaneTile {
   {
     Plan pl; pl.n = 0;
     const int q = gz - P - 1;
-    if (q >= mc.cz_begin * P && q <= mc.cz_end * P - 1) {
+    if (q >= mc.q_lo && q < mc.q_hi) {
       const int lay = q / P, k = q - lay * P;
       pl.q[0] = q; pl.os[0] = (k == P - 1) ? P - 1 + ((lay + 1) & 1) : k; pl.n = 1;
     }
@@ -568,48 +569,48 @@ struct PmgPlaneTile {
   static PMG_HD void layer(const PmgSweepParams<P> &p, const TileGeom &t, Exec &ex, double *smem, March &mc, int L)
   {
     double *Ub = smem + U_OFFSET, *Cb = smem + C_OFFSET, *Ob = smem + O_OFFSET;
+    // the layer below (L - 1) closes at this layer's vertex plane; it is written iff it belongs to the chunk
+    const bool prev_layer = L > mc.cz_first, emit_layer = L - 1 >= mc.cz_begin;
 #pragma unroll(UZ ? P : 1)
     for (int jz = 0; jz < P; ++jz) {
       const int gz = L * P + jz;
+      if (GEN && gz > mc.gz_stop) break;
       const bool last = GEN && (gz == mc.gz_last);
       const bool drain = GEN && (gz > mc.gz_last);
       const bool zero = GEN && (gz == t.zlo || gz == t.zhi);
-      // fetch plane gz + ND into the slot the previous step's y sweep read (GEN: unless it is beyond the march or a Dirichlet face)
-      const bool fetch = !GEN || (gz + ND <= mc.gz_last && gz + ND != t.zhi);
+      // fetch plane gz + ND into the slot the previous step's y sweep read, unless it is beyond the march or a Dirichlet face
+      const bool fetch = gz + ND <= mc.fetch_max;
       int fs = mc.us + ND; if (fs >= NU) fs -= NU;
       double *Ucur = Ub + mc.us * UPLANE;
       double *Ccur = Cb + mc.cur * 2 * CPLANE;
-      if (GEN && gz > mc.gz_stop) break;
       Plan pl;
       if (GEN) pl = plan_of(mc, gz);
-      else { // the plane P + 1 steps back: a plane of the chunk's own layers L - 1 (jz >= 1) or L - 2 (jz == 0)
-        pl.n = 1; pl.q[0] = gz - P - 1; pl.q[1] = 0; pl.os[1] = 0;
+      else { // the plane P + 1 steps back, if the chunk writes it: from the box plane it was put in when its layer closed
+        const int q = gz - P - 1;
+        pl.n = (q >= mc.q_lo && q < mc.q_hi) ? 1 : 0; pl.q[0] = q; pl.q[1] = 0; pl.os[1] = 0;
         pl.os[0] = (P == 1) ? ((L - 1) & 1) : (jz == 0) ? P - 1 + ((L - 1) & 1) : jz - 1;
       }
       ex.for_each_thread([&](int, ThreadState &st) {
-        load_plane(p, st, mc.up + ND * t.plane, smem, mc.base32, fs, fetch);
-        if (pl.n > 0 && !drain) epi_issue(p, t, st, pl.q[0], mc.eoff + (int64_t)(pl.q[0] - gz) * t.plane);
+        load_plane(p, st, t.plane, smem, mc.base32, fs, fetch);
+        if (pl.n > 0 && !drain) epi_issue(p, t, st, pl.q[0], mc.eq);
         if (!zero && !drain) ysweep(p, st, Ucur, Ccur);
         load_wait();
       });
       ex.sync();
       ex.for_each_thread([&](int tid, ThreadState &st) {
-        // vertex plane: the layer below (L - 1) closes; it is written iff it belongs to the chunk
-        const bool has_prev = (jz == 0) && (!GEN || L > mc.cz_first);
-        const bool emit = has_prev && (!GEN || L - 1 >= mc.cz_begin);
-        if (!drain) xzsweep(p, st, Ccur, Ob, jz, zero, has_prev, !last, emit, last && mc.top, L & 1);
+        const bool has_prev = (jz == 0) && prev_layer;
+        if (!drain) xzsweep(p, st, Ccur, Ob, jz, zero, has_prev, !last, has_prev && emit_layer, last && mc.top, L & 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
           if (i < pl.n) {
-            const int64_t eo = mc.eoff + (int64_t)(pl.q[i] - gz) * t.plane;
+            const int64_t eo = mc.eq + (int64_t)(pl.q[i] - (gz - P - 1)) * t.plane;
             if (drain || i > 0) epi_issue(p, t, st, pl.q[i], eo); // no sweep to hide behind (or the second plane of the last step)
             epilogue(p, t, st, smem, pl.os[i], pl.q[i], eo, tid);
           }
       });
       mc.cur ^= 1;
       mc.us = (mc.us + 1 == NU) ? 0 : mc.us + 1;
-      mc.eoff += t.plane;
-      mc.up += t.plane;
+      mc.eq += t.plane;
     }
   }
 
@@ -638,30 +639,29 @@ struct PmgPlaneTile {
 #endif
     mc.gz_last = mc.cz_end * P;
     mc.gz_stop = mc.gz_last + P; // the last layer's plane P - 1 leaves P + 1 steps after its own
-    mc.eoff = (int64_t)(gz_first - p.z0) * t.plane + t.tile0;
-    mc.up = p.u + (int64_t)(gz_first - p.z0) * t.plane;
+    mc.fetch_max = (t.zhi >= 0 && t.zhi <= mc.gz_last) ? t.zhi - 1 : mc.gz_last;
+    mc.q_lo = mc.cz_begin * P > p.z_own_lo ? mc.cz_begin * P : p.z_own_lo;
+    mc.q_hi = mc.cz_end * P < p.z_own_hi ? mc.cz_end * P : p.z_own_hi;
+    mc.eq = (int64_t)(gz_first - P - 1 - p.z0) * t.plane + t.tile0;
+    const double *up = p.u + (int64_t)(gz_first - p.z0) * t.plane;
 
-    ex.for_each_thread([&](int tid, ThreadState &st) { decode(p, t, tid, st, smem); });
+    ex.for_each_thread([&](int tid, ThreadState &st) { decode(p, t, tid, st, smem); st.ld_src = up + st.ld_off; });
     ex.sync();
     ex.for_each_thread([&](int, ThreadState &st) {
       // planes gz_first .. gz_first + ND - 1 -> slots 0 .. ND - 1, a group each; the first plane has arrived after the wait
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
         const int gz = gz_first + d;
-        load_plane(p, st, mc.up + d * t.plane, smem, mc.base32, d, gz <= mc.gz_last && gz != t.zlo && gz != t.zhi);
+        load_plane(p, st, t.plane, smem, mc.base32, d, gz <= mc.fetch_max && gz != t.zlo);
       }
       load_wait();
     });
     ex.sync();
-    // interior layers of the chunk: no flag to look at.  Planes L P .. L P + P + ND - 1 (those the steps fetch included) hold no
-    // Dirichlet face and lie inside the march, the layer below is the chunk's own.
-    const int fast_lo = mc.cz_begin + 2; // the layers below L and L - 1 are the chunk's own
-    int fast_hi = mc.cz_end;                                    // exclusive
-    if (fast_hi > p.nz - 1) fast_hi = p.nz - 1;
-    // the steps after the chunk's top vertex plane are drain steps: no plane, only the epilogues that are still due
+    // Layers without a Dirichlet plane, before the chunk's top vertex plane: the steps look at a handful of uniform flags only
+    // (GEN = false).  The others -- the mesh's bottom layer under a Dirichlet face, the top vertex plane and the drain steps
+    // after it -- take the general path.
     for (int L = mc.cz_first; L * P <= mc.gz_stop; ++L) {
-      const int gmax = L * P + P - 1 + ND; // the farthest plane a step of the layer fetches
-      const bool fast = L >= fast_lo && L < fast_hi && gmax <= mc.gz_last && (t.zhi < 0 || gmax < t.zhi);
+      const bool fast = L < mc.cz_end && L * P > t.zlo && (t.zhi < 0 || L * P + P - 1 < t.zhi);
       if (fast) layer<false>(p, t, ex, smem, mc, L);
       else layer<true>(p, t, ex, smem, mc, L);
     }

@@ -105,10 +105,19 @@ int PMG_PLANE_CAT(pmg_plane_dispatch_m, PMG_PLANE_TU_MODE)(const pmgk_level *lv,
                                                            double *out, double f1, double f2, cudaStream_t s, int *geom)
 {
   switch (lv->degree) {
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ) \
+#define PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ) \
   case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom);
+#if PMG_PLANE_TU_MODE == 0
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ)
+#else
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ)
+#endif
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE
+#undef PMG_PLANE_CASE_F
+#undef PMG_PLANE_LAUNCH
     default: return PMG_ERR_UNSUPPORTED;
   }
 }

@@ -93,10 +93,23 @@ extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, un
     }
     return -3;
   }
-  switch (degree) {
+  // the shipped tiles: the plain apply's for mode 0, the fused modes' otherwise
+  if (mode == 0) {
+    switch (degree) {
 #define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ) case P: plane_go<P, BX, BY, NT, UZ>(ARGS); return 0;
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ)
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE
+#undef PMG_PLANE_CASE_F
+    }
+  } else {
+    switch (degree) {
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ) case P: plane_go<P, BX, BY, NT, UZ>(ARGS); return 0;
+#include "pmg_apply_plane_tiles.inc"
+#undef PMG_PLANE_CASE
+#undef PMG_PLANE_CASE_F
+    }
   }
   return -3;
 }

@@ -67,6 +67,11 @@ __global__ void __launch_bounds__(Tile::NT, 1) refkern(const __grid_constant__ P
   Tile::run(p, ex, sm, b % p.tiles_x, (b / p.tiles_x) % p.tiles_y, b / (p.tiles_x * p.tiles_y));
 }
 #endif
+__global__ void fill(double *a, size_t n, unsigned mul, unsigned add, unsigned mod)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    a[i] = (double)(((unsigned)i * mul + add) % mod) / (double)mod - 0.5;
+}
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
 static int choose_chunks(int tiles, int n, int slots, int chunks_arg, int *lpc)
@@ -121,20 +126,14 @@ int main(int argc, char **argv)
   pmg_fe_pencil(P, M, K);
   pmg_sweep_fill_matrices<P>(p, M, K, h);
   const size_t N = (size_t)p.Nx * p.Ny * p.Nz;
-  std::vector<double> hu(N), hb(N), hx(N);
-  for (size_t i = 0; i < N; ++i) {
-    hu[i] = (double)((i * 2654435761u) % 1000) / 1000.0 - 0.5;
-    hb[i] = (double)((i * 40503u + 17) % 997) / 997.0 - 0.5;
-    hx[i] = (double)((i * 69069u + 5) % 991) / 991.0 - 0.5;
-  }
   double *u, *b, *xo, *out, *tab, *ref;
   const size_t bytes = N * 8 + 8 * (size_t)p.Nx + 16;
   CK(cudaMalloc(&u, bytes)); CK(cudaMalloc(&b, bytes)); CK(cudaMalloc(&xo, bytes)); CK(cudaMalloc(&out, bytes)); CK(cudaMalloc(&ref, bytes));
   std::vector<double> htab(1000);
   for (int i = 0; i < 1000; ++i) htab[i] = 0.5 + 0.001 * i;
   CK(cudaMalloc(&tab, 1000 * 8)); CK(cudaMemcpy(tab, htab.data(), 8000, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(u, hu.data(), N * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(b, hb.data(), N * 8, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(xo, hx.data(), N * 8, cudaMemcpyHostToDevice));
+  fill<<<1184, 256>>>(u, N, 2654435761u, 0u, 1000u); fill<<<1184, 256>>>(b, N, 40503u, 17u, 997u); fill<<<1184, 256>>>(xo, N, 69069u, 5u, 991u);
+  CK(cudaDeviceSynchronize());
   p.u = u; p.b = b; p.xold = xo; p.out = out; p.f1 = 0.3; p.f2 = 0.1; p.dinv_tab = tab; p.dinv_vec = nullptr;
   const char *name = STR(C_NAME);
   run_mode<0>(p, n, reps, chunks, name, N);
@@ -164,7 +163,7 @@ int main(int argc, char **argv)
 #ifdef WITH_REF
   {
     // one clean fused step into `out` from fresh x_old, compared with the line-marching kernel
-    CK(cudaMemcpy(xo, hx.data(), N * 8, cudaMemcpyHostToDevice));
+    fill<<<1184, 256>>>(xo, N, 69069u, 5u, 991u);
     PmgSweepParams<P> q = p; q.out = out; q.mode = 3;
     using Tile = TileT<3>;
     q.tiles_x = Tile::tiles_of(n, true, C_BX); q.tiles_y = Tile::tiles_of(n, true, C_BY); q.n_chunks = 2; q.layers_per_chunk = (n + 1) / 2;
