@@ -59,13 +59,18 @@ static int launch(const pmgk_level *lv, int mode, const double *u, const double 
   p.tiles_x = (lv->nx + BX - 1) / BX;
   p.tiles_y = (lv->ny + BY - 1) / BY;
   const int smem_bytes = Tile::SMEM_DOUBLES * (int)sizeof(double);
-  static int configured = 0;
-  static int ctas_per_sm = 1;
-  if (!configured) {
+  // per device: the shared-memory opt-in and the occupancy belong to the device the launch goes to
+  enum { MAXDEV = 64 };
+  static int ctas_per_sm_dev[MAXDEV];
+  int dev = 0;
+  PMG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAXDEV) return PMG_ERR_UNSUPPORTED;
+  int ctas_per_sm = __atomic_load_n(&ctas_per_sm_dev[dev], __ATOMIC_ACQUIRE);
+  if (ctas_per_sm == 0) {
     PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_apply_kernel<P, BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_apply_kernel<P, BX, BY, MINB>, Tile::NT, smem_bytes));
     if (ctas_per_sm < 1) return PMG_ERR_CUDA;
-    configured = 1;
+    __atomic_store_n(&ctas_per_sm_dev[dev], ctas_per_sm, __ATOMIC_RELEASE);
   }
   const int slots = pmgk_device_sm_count() * ctas_per_sm;
   choose_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, &p.n_chunks, &p.layers_per_chunk);
@@ -112,7 +117,7 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
 {
   const int64_t n_loc = (int64_t)lv->Nx * lv->Ny * lv->nzl;
   const bool sweep_kernel = lv->dim == 3 && !lv->coef && (part != PMGK_PART_ALL || lv->degree > PMG_PLANE_MAX_DEGREE || lv->tile_variant != 0) &&
-                            (lv->tile_variant == 1 || lv->tile_variant == 6 || lv->tile_variant == 4 || lv->tile_variant == 5 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
+                            (lv->tile_variant == 1 || lv->tile_variant == 6 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
   if (part != PMGK_PART_ALL && !sweep_kernel) return PMG_ERR_UNSUPPORTED; /* only the line-marching kernel launches in parts */
   if (lv->dim == 2) return pmg_dim2_apply(lv, mode, u, b, xold, out, f1, f2, s, geom);
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
@@ -121,9 +126,7 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
      kernel (direct loads, no staging prologue) for the small coarse levels, where launch-to-result latency is everything:
      measured on B200 (tools/small_levels.py) 5.6-7.2 us against 7.0-12.3 us per fused step for Q1 up to 32^3 cells and
      12.3 against 16.4 us for Q2 on 32^3; from 64^3 cells on the line-marching kernel wins (14.3 : 17.1, 38.9 : 55.3 us).
-     1 = line-marching always; 2, 3 = cell-tile always (small / large tiles); 4, 5 = line-marching always, in its pipelined form
-     for degrees 1..5 (csrc/pmg_apply_sweep_pipe.h: experimental, not yet measured on the GPU; 5 = b / x_old of the fused modes read
-     from global memory instead of shared-memory boxes). */
+     1 = line-marching always; 2, 3 = cell-tile always (small / large tiles); 6 = plane-per-step kernel always. */
   const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
   const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
   /* round 2: the plane-per-step kernel (csrc/pmg_apply_plane.h) takes the large levels of degrees 1..6 (measured at 100 M DoFs,
@@ -139,7 +142,7 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
       default: return PMG_ERR_ARG;
     }
   }
-  if (lv->tile_variant == 1 || lv->tile_variant == 6 /* degrees 7, 8: the line-marching kernel */ || lv->tile_variant == 4 || lv->tile_variant == 5 || (lv->tile_variant == 0 && !small_level)) {
+  if (lv->tile_variant == 1 || lv->tile_variant == 6 /* degrees 7, 8: the line-marching kernel */ || (lv->tile_variant == 0 && !small_level)) {
     switch (mode) { /* one kernel per epilogue mode: csrc/pmg_apply_sweep_m<mode>.cu */
       case PMGK_APPLY: return pmg_sweep_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom, part);
       case PMGK_RESIDUAL: return pmg_sweep_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom, part);

@@ -2,8 +2,6 @@
 // epilogue mode.  Included by pmg_apply_sweep_m{0,1,2,3}.cu, each of which defines PMG_SWEEP_TU_MODE (the PmgApplyMode the
 // translation unit is compiled for) and so provides pmg_sweep_dispatch_m<mode>(); four translation units compile in parallel.
 #include "pmg_apply_sweep.h"
-#include "pmg_apply_sweep_pipe.h"
-#include <type_traits>
 #include "pmg_cuda_common.h"
 #include "pmg_kernels.h"
 
@@ -24,21 +22,6 @@ __global__ void __launch_bounds__(NT, MINB)
 pmg_sweep_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
   using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>;
-  extern __shared__ __align__(128) double pmg_sweep_smem[];
-  PmgSweepDeviceExec<Tile> ex;
-  const int b = blockIdx.x;
-  const int tile_x = b % p.tiles_x;
-  const int tile_y = (b / p.tiles_x) % p.tiles_y;
-  const int chunk = chunk_first + (b / (p.tiles_x * p.tiles_y)) * chunk_stride;
-  Tile::run(p, ex, pmg_sweep_smem, tile_x, tile_y, chunk);
-}
-
-// the pipelined variant (csrc/pmg_apply_sweep_pipe.h, opt-in: PMG_TILE_VARIANT=4): two groups of NG threads per CTA
-template <int P, int BX, int BY, int LZ, int NG, int MINB, int US, int FM, int RL, int EG>
-__global__ void __launch_bounds__(2 * NG, MINB)
-pmg_sweep_pipe_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
-{
-  using Tile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL, EG>;
   extern __shared__ __align__(128) double pmg_sweep_smem[];
   PmgSweepDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -74,14 +57,12 @@ void choose_sweep_chunks(int tiles, int layers, int slots, int degree, int min_c
 template <int P, int FM> struct PmgSweepModeTune { static constexpr int roll = 0, min_ctas = 0; };
 template <> struct PmgSweepModeTune<4, PMG_MODE_APPLY> { static constexpr int roll = 1, min_ctas = 4; };
 
-template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL, bool PIPE = false, int EG = 0>
+template <int P, int BX, int BY, int LZ, int NT, int MINB, int US, int FM, int RL>
 int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1,
                  double f2, cudaStream_t stream, int *geom, int part)
 {
-  using Tile = std::conditional_t<PIPE, PmgSweepPipe<P, BX, BY, LZ, NT, US, FM, RL, EG>, PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>>;
-  void (*kernel)(const PmgSweepParams<P>, int, int);
-  if constexpr (PIPE) kernel = pmg_sweep_pipe_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL, EG>;
-  else kernel = pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>;
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, FM, 1, RL>;
+  void (*kernel)(const PmgSweepParams<P>, int, int) = pmg_sweep_kernel<P, BX, BY, LZ, NT, MINB, US, FM, RL>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
   p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
@@ -94,13 +75,18 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
   // APPLY stages only u; the other modes also stage the epilogue's b / x_old rows
   constexpr bool epi = (FM != PMG_MODE_APPLY);
   const int smem_bytes = Tile::smem_doubles(epi) * (int)sizeof(double);
-  static int configured = 0;
-  static int ctas_per_sm = 1;
-  if (!configured) {
+  // per device: the shared-memory opt-in and the occupancy belong to the device the launch goes to
+  enum { MAXDEV = 64 };
+  static int ctas_per_sm_dev[MAXDEV];
+  int dev = 0;
+  PMG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAXDEV) return PMG_ERR_UNSUPPORTED;
+  int ctas_per_sm = __atomic_load_n(&ctas_per_sm_dev[dev], __ATOMIC_ACQUIRE);
+  if (ctas_per_sm == 0) {
     PMG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, Tile::NT, smem_bytes));
     if (ctas_per_sm < 1) return PMG_ERR_CUDA;
-    configured = 1;
+    __atomic_store_n(&ctas_per_sm_dev[dev], ctas_per_sm, __ATOMIC_RELEASE);
   }
   const int slots = pmgk_device_sm_count() * ctas_per_sm;
   // a launch in parts (PMG_HALO_OVERLAP=1, host/pmg_operator.c) needs at least three chunks: the first and the last read the
@@ -125,21 +111,6 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
   return 0;
 }
 
-// the pipelined variant with the same tile, NG = the table's thread count per group; CTAs per SM as shared memory allows
-template <int P, int BX, int BY, int LZ, int NG, int US, int FM, int EG>
-int launch_sweep_pipe(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
-                      cudaStream_t stream, int *geom, int part)
-{
-  if constexpr (P <= 5) {
-    constexpr int RL = (P >= 4); // rolled cell loops: the two groups' register budgets add up
-    using PipeTile = PmgSweepPipe<P, BX, BY, LZ, NG, US, FM, RL, EG>;
-    constexpr int minb = (PipeTile::smem_doubles(FM != PMG_MODE_APPLY) * 8 + 1024 <= 113 * 1024) ? 2 : 1;
-    return launch_sweep<P, BX, BY, LZ, NG, minb, US, FM, RL, true, EG>(lv, u, b, xold, out, f1, f2, stream, geom, part);
-  } else {
-    return PMG_ERR_UNSUPPORTED;
-  }
-}
-
 } // namespace
 
 #define PMG_SWEEP_CAT2(a, b) a##b
@@ -148,20 +119,6 @@ int launch_sweep_pipe(const pmgk_level *lv, const double *u, const double *b, co
 int PMG_SWEEP_CAT(pmg_sweep_dispatch_m, PMG_SWEEP_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
                                                            double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
-  if (lv->tile_variant == 4 || lv->tile_variant == 5) {
-    /* opt-in: the pipelined variant; degrees 1..5 (above, its buffers do not fit shared memory); 5 = with b / x_old read from
-       global memory by the z sweep (EG = 1; the same kernel as 4 for the plain apply) */
-    constexpr int eg = (PMG_SWEEP_TU_MODE != PMG_MODE_APPLY);
-    switch (lv->degree) {
-#define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
-  case P: if (P <= 5) return lv->tile_variant == 5 ? launch_sweep_pipe<P, BX, BY, LZ, NT, US, PMG_SWEEP_TU_MODE, eg>(lv, u, b, xold, out, f1, f2, s, geom, part) \
-                                                     : launch_sweep_pipe<P, BX, BY, LZ, NT, US, PMG_SWEEP_TU_MODE, 0>(lv, u, b, xold, out, f1, f2, s, geom, part); \
-    break;
-#include "pmg_apply_sweep_tiles.inc"
-#undef PMG_SWEEP_CASE
-      default: break;
-    }
-  }
   switch (lv->degree) {
 #define PMG_SWEEP_CASE(P, BX, BY, LZ, NT, MINB, US) \
   case P: return launch_sweep<P, BX, BY, LZ, NT, (PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::min_ctas ? PmgSweepModeTune<P, PMG_SWEEP_TU_MODE>::min_ctas : MINB), \

@@ -60,13 +60,18 @@ int launch_var(const pmgk_level *lv, int mode, const double *u, const double *b,
   p.tiles_x = (lv->nx + BX - 1) / BX;
   p.tiles_y = (lv->ny + BY - 1) / BY;
   const int smem_bytes = Tile::SMEM_DOUBLES * (int)sizeof(double);
-  static int configured = 0;
-  static int ctas_per_sm = 1;
-  if (!configured) {
+  // per device: the shared-memory opt-in and the occupancy belong to the device the launch goes to
+  enum { MAXDEV = 64 };
+  static int ctas_per_sm_dev[MAXDEV];
+  int dev = 0;
+  PMG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAXDEV) return PMG_ERR_UNSUPPORTED;
+  int ctas_per_sm = __atomic_load_n(&ctas_per_sm_dev[dev], __ATOMIC_ACQUIRE);
+  if (ctas_per_sm == 0) {
     PMG_CUDA_CHECK(cudaFuncSetAttribute(pmg_var_kernel<P, BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     PMG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, pmg_var_kernel<P, BX, BY, MINB>, Tile::NT, smem_bytes));
     if (ctas_per_sm < 1) return PMG_ERR_CUDA;
-    configured = 1;
+    __atomic_store_n(&ctas_per_sm_dev[dev], ctas_per_sm, __ATOMIC_RELEASE);
   }
   const int slots = pmgk_device_sm_count() * ctas_per_sm;
   choose_var_chunks(p.tiles_x * p.tiles_y, lv->cz_hi - lv->cz_lo, slots, &p.n_chunks, &p.layers_per_chunk);

@@ -16,7 +16,8 @@ int g_sm_count = 0;
 inline int blocks_for(int64_t n)
 {
   int64_t b = (n + kThreads - 1) / kThreads;
-  const int cap = (g_sm_count > 0 ? g_sm_count : 148) * 8;
+  int cap = (g_sm_count > 0 ? g_sm_count : 148) * 8;
+  if (cap > kMaxBlocks) cap = kMaxBlocks; // the reductions' work buffer holds kMaxBlocks partial sums
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;

@@ -33,12 +33,23 @@ void pmg_set_error(const char *fmt, ...)
   va_end(ap);
 }
 
-void pmg_count_launch(int n) { g_launches += n; }
+void pmg_count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+
+int pmg_enter(const pmg_context *ctx)
+{
+  if (!ctx) return PMG_ERR_ARG;
+  int d = -1;
+  if (cudaGetDevice(&d) == cudaSuccess && d == ctx->device) return PMG_OK;
+  PMG_CUDA(cudaSetDevice(ctx->device));
+  return PMG_OK;
+}
 
 const char *pmg_last_error(void) { return tls_error; }
 const char *pmg_version(void) { return "portable-multigrid_b200 0.1 (sm_100a)"; }
 
 /* ---- context -------------------------------------------------------------- */
+static int context_init(pmg_context *ctx, const void *nccl_id);
+
 static int context_common(pmg_context **out, int device, int rank, int n_ranks, const void *nccl_id)
 {
   if (!out || n_ranks < 1 || rank < 0 || rank >= n_ranks) { pmg_set_error("pmg_context_create: bad arguments"); return PMG_ERR_ARG; }
@@ -48,11 +59,21 @@ static int context_common(pmg_context **out, int device, int rank, int n_ranks, 
     return PMG_ERR_CUDA;
   }
   if (device < 0 || device >= ndev) { pmg_set_error("device %d out of range (%d devices)", device, ndev); return PMG_ERR_ARG; }
+  if (n_ranks > 1 && !nccl_id) { pmg_set_error("distributed context needs an ncclUniqueId"); return PMG_ERR_ARG; }
   PMG_CUDA(cudaSetDevice(device));
   pmg_context *ctx = (pmg_context *)calloc(1, sizeof(*ctx));
   if (!ctx) return PMG_ERR_NOMEM;
   ctx->device = device; ctx->rank = rank; ctx->n_ranks = n_ranks;
   ctx->coarse_threshold = 262144;
+  const int rc = context_init(ctx, nccl_id);
+  if (rc != PMG_OK) { pmg_context_destroy(ctx); return rc; } /* destroy releases whatever was created */
+  *out = ctx;
+  return PMG_OK;
+}
+
+static int context_init(pmg_context *ctx, const void *nccl_id)
+{
+  const int rank = ctx->rank, n_ranks = ctx->n_ranks;
   PMG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   PMG_CUDA(cudaMalloc((void **)&ctx->work, sizeof(double) * (size_t)pmgk_dot_work_doubles()));
   PMG_CUDA(cudaMalloc((void **)&ctx->scalars, sizeof(double) * 64));
@@ -60,7 +81,6 @@ static int context_common(pmg_context **out, int device, int rank, int n_ranks, 
   PMG_CUDA(cudaMallocHost((void **)&ctx->h_scalars, sizeof(double) * 64));
   ctx->sm_count = pmgk_device_sm_count();
   if (n_ranks > 1) {
-    if (!nccl_id) { pmg_set_error("distributed context needs an ncclUniqueId"); return PMG_ERR_ARG; }
     ncclUniqueId id;
     memcpy(&id, nccl_id, sizeof(id));
     PMG_NCCL(ncclCommInitRank(&ctx->comm, n_ranks, id, rank));
@@ -78,7 +98,6 @@ static int context_common(pmg_context **out, int device, int rank, int n_ranks, 
       ctx->overlap = 1;
     }
   }
-  *out = ctx;
   return PMG_OK;
 }
 
@@ -102,7 +121,7 @@ int pmg_context_destroy(pmg_context *ctx)
 {
   if (!ctx) return PMG_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->overlap) {
     cudaStreamSynchronize(ctx->halo_stream);
     ncclCommDestroy(ctx->halo_comm);
@@ -111,7 +130,7 @@ int pmg_context_destroy(pmg_context *ctx)
   }
   if (ctx->has_comm) ncclCommDestroy(ctx->comm);
   cudaFree(ctx->work); cudaFree(ctx->scalars); cudaFreeHost(ctx->h_scalars);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   free(ctx);
   return PMG_OK;
 }
@@ -139,7 +158,8 @@ int pmg_context_set_coarse_threshold(pmg_context *ctx, int64_t n_dofs)
 }
 
 void *pmg_context_stream(pmg_context *ctx) { return ctx ? (void *)ctx->stream : NULL; }
-int64_t pmg_context_launch_count(const pmg_context *ctx) { (void)ctx; return g_launches; }
+/* kernels and collectives this PROCESS has enqueued (all contexts, all threads; the counter is atomic) */
+int64_t pmg_context_launch_count(const pmg_context *ctx) { (void)ctx; return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 /* ---- partition -------------------------------------------------------------- */
 /* A level is cut into n_ranks z-slabs of nz / n_ranks cell layers iff n_ranks divides nz.
@@ -208,6 +228,7 @@ int pmg_layout_same(const pmg_layout *a, const pmg_layout *b)
 /* ---- vectors ---------------------------------------------------------------- */
 int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector **out)
 {
+  if (ctx) PMG_CHECK(pmg_enter(ctx));
   pmg_vector *v = (pmg_vector *)calloc(1, sizeof(*v));
   if (!v) return PMG_ERR_NOMEM;
   v->ctx = ctx; v->lay = *lay;
@@ -287,30 +308,35 @@ static int check_pair(const pmg_vector *a, const pmg_vector *b)
 
 int pmg_vector_set(pmg_vector *v, double value)
 {
+  if (v) PMG_CHECK(pmg_enter(v->ctx));
   if (!v) return PMG_ERR_ARG;
   return pmgk_set(v->d, value, v->lay.n_local, v->ctx->stream);
 }
 
 int pmg_vector_copy(pmg_vector *dst, const pmg_vector *src)
 {
+  if (dst) PMG_CHECK(pmg_enter(dst->ctx));
   PMG_CHECK(check_pair(dst, src));
   return pmgk_copy(dst->d, src->d, dst->lay.n_local, dst->ctx->stream);
 }
 
 int pmg_vector_scale(pmg_vector *v, double a)
 {
+  if (v) PMG_CHECK(pmg_enter(v->ctx));
   if (!v) return PMG_ERR_ARG;
   return pmgk_scale(v->d, a, v->lay.n_local, v->ctx->stream);
 }
 
 int pmg_vector_add(pmg_vector *v, double a, const pmg_vector *x)
 {
+  if (v) PMG_CHECK(pmg_enter(v->ctx));
   PMG_CHECK(check_pair(v, x));
   return pmgk_axpby(v->d, 1.0, v->d, a, x->d, v->lay.n_local, v->ctx->stream);
 }
 
 int pmg_vector_sadd(pmg_vector *v, double s, double a, const pmg_vector *x)
 {
+  if (v) PMG_CHECK(pmg_enter(v->ctx));
   PMG_CHECK(check_pair(v, x));
   return pmgk_axpby(v->d, s, v->d, a, x->d, v->lay.n_local, v->ctx->stream);
 }
@@ -334,6 +360,7 @@ static int fetch_scalar(pmg_context *ctx, int slot, double *result)
 
 int pmg_vector_dot(const pmg_vector *x, const pmg_vector *y, double *result)
 {
+  if (x) PMG_CHECK(pmg_enter(x->ctx));
   PMG_CHECK(check_pair(x, y));
   if (!result) return PMG_ERR_ARG;
   pmg_context *ctx = x->ctx;
@@ -378,12 +405,12 @@ int pmg_halo_update_on(pmg_context *ctx, const pmg_layout *lay, double *d, ncclC
   PMG_NCCL(ncclGroupStart());
   if (lay->upper >= 0) {
     /* my top p owned planes -> upper neighbour's lower ghost layer; its first owned plane -> my upper ghost */
-    PMG_NCCL(ncclSend(d + plane * (lay->z_own_hi - p - lay->z0), (size_t)(plane * p), ncclDouble, lay->upper, comm, stream));
-    PMG_NCCL(ncclRecv(d + plane * (lay->z_own_hi - lay->z0), (size_t)plane, ncclDouble, lay->upper, comm, stream));
+    PMG_NCCL_IN_GROUP(ncclSend(d + plane * (lay->z_own_hi - p - lay->z0), (size_t)(plane * p), ncclDouble, lay->upper, comm, stream));
+    PMG_NCCL_IN_GROUP(ncclRecv(d + plane * (lay->z_own_hi - lay->z0), (size_t)plane, ncclDouble, lay->upper, comm, stream));
   }
   if (lay->lower >= 0) {
-    PMG_NCCL(ncclSend(d + plane * (lay->z_own_lo - lay->z0), (size_t)plane, ncclDouble, lay->lower, comm, stream));
-    PMG_NCCL(ncclRecv(d, (size_t)(plane * p), ncclDouble, lay->lower, comm, stream));
+    PMG_NCCL_IN_GROUP(ncclSend(d + plane * (lay->z_own_lo - lay->z0), (size_t)plane, ncclDouble, lay->lower, comm, stream));
+    PMG_NCCL_IN_GROUP(ncclRecv(d, (size_t)(plane * p), ncclDouble, lay->lower, comm, stream));
   }
   PMG_NCCL(ncclGroupEnd());
   pmg_count_launch(1);
@@ -421,12 +448,12 @@ int pmg_vector_compress_add(pmg_vector *v)
   double *from_upper = tmp, *from_lower = tmp + plane * p;
   PMG_NCCL(ncclGroupStart());
   if (l->upper >= 0) {
-    PMG_NCCL(ncclSend(v->d + plane * (l->z_own_hi - l->z0), (size_t)plane, ncclDouble, l->upper, ctx->comm, ctx->stream));
-    PMG_NCCL(ncclRecv(from_upper, (size_t)(plane * p), ncclDouble, l->upper, ctx->comm, ctx->stream));
+    PMG_NCCL_IN_GROUP(ncclSend(v->d + plane * (l->z_own_hi - l->z0), (size_t)plane, ncclDouble, l->upper, ctx->comm, ctx->stream));
+    PMG_NCCL_IN_GROUP(ncclRecv(from_upper, (size_t)(plane * p), ncclDouble, l->upper, ctx->comm, ctx->stream));
   }
   if (l->lower >= 0) {
-    PMG_NCCL(ncclSend(v->d, (size_t)(plane * p), ncclDouble, l->lower, ctx->comm, ctx->stream));
-    PMG_NCCL(ncclRecv(from_lower, (size_t)plane, ncclDouble, l->lower, ctx->comm, ctx->stream));
+    PMG_NCCL_IN_GROUP(ncclSend(v->d, (size_t)(plane * p), ncclDouble, l->lower, ctx->comm, ctx->stream));
+    PMG_NCCL_IN_GROUP(ncclRecv(from_lower, (size_t)plane, ncclDouble, l->lower, ctx->comm, ctx->stream));
   }
   PMG_NCCL(ncclGroupEnd());
   pmg_count_launch(1);
@@ -495,6 +522,7 @@ int pmg_vector_import_host(pmg_vector *v, const double *host)
   if (!l->active) return PMG_OK;
   /* every stored plane (owned and ghost) is filled from the global array */
   PMG_CUDA(cudaMemcpyAsync(v->d, host + l->plane * l->z0, sizeof(double) * (size_t)l->n_local, cudaMemcpyHostToDevice, v->ctx->stream));
+  PMG_CUDA(cudaStreamSynchronize(v->ctx->stream)); /* the caller may reuse `host` (pinned or not) as soon as this returns */
   return PMG_OK;
 }
 

@@ -14,6 +14,9 @@ extern "C" {
 
 void pmg_set_error(const char *fmt, ...);
 void pmg_count_launch(int n);
+/* every public entry point that enqueues work makes the context's device current first (a caller thread may have switched
+   devices, or hold contexts on several GPUs) */
+int pmg_enter(const pmg_context *ctx);
 
 #define PMG_CHECK(call)                        \
   do {                                         \
@@ -27,6 +30,17 @@ void pmg_count_launch(int n);
     if (pmg_e_ != cudaSuccess) {                                                                  \
       pmg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(pmg_e_)); \
       return PMG_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+/* inside ncclGroupStart() .. ncclGroupEnd(): a failing call closes the group before the function returns */
+#define PMG_NCCL_IN_GROUP(call)                                                                   \
+  do {                                                                                            \
+    ncclResult_t pmg_n_ = (call);                                                                 \
+    if (pmg_n_ != ncclSuccess) {                                                                  \
+      pmg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, ncclGetErrorString(pmg_n_)); \
+      ncclGroupEnd();                                                                             \
+      return PMG_ERR_NCCL;                                                                        \
     }                                                                                             \
   } while (0)
 

@@ -115,6 +115,7 @@ static int check_vec(const pmg_operator *op, const pmg_vector *v, const char *wh
 /* ghost update of u followed by the fused apply (every operator application of the path goes through here) */
 int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1, double f2)
 {
+  if (op) PMG_CHECK(pmg_enter(op->ctx));
   pmg_context *ctx = op->ctx;
   if (!op->lay.active) return PMG_OK;
   /* src.update_ghost_values() (:661); there is no compress(add): the kernel owns complete rows */

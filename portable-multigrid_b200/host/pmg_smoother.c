@@ -43,11 +43,21 @@ int pmg_chebyshev_destroy(pmg_chebyshev *s)
   return PMG_OK;
 }
 
+/* lmax: the largest eigenvalue as the smoother uses it (the estimate times its safety factor, or the configured value) */
+static int chebyshev_parameters(double lmin, double lmax, double smoothing_range, int degree_in, double *theta, double *delta,
+                                int *degree_out);
+
 int pmg_host_chebyshev_parameters(double lmin, double lmax_est, double smoothing_range, int degree_in,
                                   double *theta, double *delta, int *degree_out)
 {
   if (!theta || !delta || !degree_out) return PMG_ERR_ARG;
-  const double lmax = 1.2 * lmax_est; /* safety factor: CG is in general not converged */
+  return chebyshev_parameters(lmin, 1.2 * lmax_est /* safety factor: CG is in general not converged */, smoothing_range, degree_in,
+                              theta, delta, degree_out);
+}
+
+static int chebyshev_parameters(double lmin, double lmax, double smoothing_range, int degree_in, double *theta, double *delta,
+                                int *degree_out)
+{
   const double alpha = (smoothing_range > 1.0) ? lmax / smoothing_range : fmin(0.9 * lmax, lmin);
   int degree = degree_in;
   if (degree == PMG_INVALID_DEGREE) {
@@ -105,69 +115,93 @@ int pmg_host_tridiag_extreme_eigenvalues(int n, const double *diag, const double
 /* PreconditionChebyshev::estimate_eigenvalues: Jacobi-preconditioned CG on A x = v from x = 0 with
    v_i = (global_i mod 11) - mean, IterationNumberControl(eig_cg_n_iterations, 1e-10); eigenvalues of the
    Lanczos matrix of iterations 1..it-1. */
-int pmg_chebyshev_estimate(pmg_chebyshev *s)
+/* the Lanczos part: every resource is released on every path */
+static int estimate_lanczos(pmg_chebyshev *s, double *lmin, double *lmax)
 {
   pmg_operator *op = s->op;
   pmg_context *ctx = op->ctx;
   const pmg_layout *l = &op->lay;
+  pmg_vector *r = NULL, *z = NULL, *pv = NULL, *Ap = NULL;
+  double *diag = NULL, *off = NULL;
+  int rc = PMG_OK, nt = 0, it = 0;
+#define EST_CHECK(call) do { rc = (call); if (rc != PMG_OK) goto done; } while (0)
+  const int max_it = s->eig_cg_n_iterations;
+  /* one entry per iteration; the coarsest level asks for "as many as it takes" (up to 2^31): grow on demand */
+  size_t cap = (size_t)(max_it < 4096 ? max_it : 4096) + 2;
+  diag = (double *)calloc(cap, sizeof(double));
+  off = (double *)calloc(cap, sizeof(double));
+  if (!diag || !off) { pmg_set_error("chebyshev estimate: out of host memory"); rc = PMG_ERR_NOMEM; goto done; }
+  EST_CHECK(pmg_vector_create_layout(ctx, l, &r));
+  EST_CHECK(pmg_vector_create_layout(ctx, l, &z));
+  EST_CHECK(pmg_vector_create_layout(ctx, l, &pv));
+  EST_CHECK(pmg_vector_create_layout(ctx, l, &Ap));
+  /* start vector on all stored planes (global index => identical on any rank count) */
+  EST_CHECK(pmgk_set_mod11(r->d, l->plane * l->z0, l->n_local, ctx->stream));
+  double mean = 0.0, res = 0.0, rz = 0.0;
+  EST_CHECK(pmg_vector_mean_value(r, &mean));
+  EST_CHECK(pmgk_set(z->d, -mean, l->n_local, ctx->stream));
+  EST_CHECK(pmg_vector_add(r, 1.0, z)); /* r = v - mean */
+  EST_CHECK(pmg_vector_l2_norm(r, &res));
+  if (res > 1e-10) {
+    EST_CHECK(pmgk_scale_dinv(&op->lv, 1.0, r->d, z->d, ctx->stream));
+    EST_CHECK(pmg_vector_copy(pv, z));
+    EST_CHECK(pmg_vector_dot(r, z, &rz));
+    double alpha_prev = 0.0, beta_prev = 0.0, eigen_beta_alpha = 0.0;
+    for (;;) {
+      ++it;
+      EST_CHECK(pmg_laplace_operator_vmult(op, Ap, pv));
+      double pAp = 0.0;
+      EST_CHECK(pmg_vector_dot(pv, Ap, &pAp));
+      const double alpha = rz / pAp;
+      EST_CHECK(pmg_vector_add(r, -alpha, Ap));
+      EST_CHECK(pmg_vector_l2_norm(r, &res));
+      if (it > 1) {
+        if ((size_t)nt + 2 > cap) {
+          const size_t ncap = 2 * cap;
+          double *nd = (double *)realloc(diag, ncap * sizeof(double)), *no = nd ? (double *)realloc(off, ncap * sizeof(double)) : NULL;
+          if (nd) diag = nd;
+          if (no) off = no;
+          if (!nd || !no) { pmg_set_error("chebyshev estimate: out of host memory"); rc = PMG_ERR_NOMEM; goto done; }
+          cap = ncap;
+        }
+        diag[nt] = 1.0 / alpha_prev + eigen_beta_alpha;
+        eigen_beta_alpha = beta_prev / alpha_prev;
+        off[nt] = sqrt(beta_prev) / alpha_prev;
+        ++nt;
+      }
+      if (res <= 1e-10 || it >= max_it) break;
+      EST_CHECK(pmgk_scale_dinv(&op->lv, 1.0, r->d, z->d, ctx->stream));
+      double rz_new = 0.0;
+      EST_CHECK(pmg_vector_dot(r, z, &rz_new));
+      const double beta = rz_new / rz;
+      EST_CHECK(pmg_vector_sadd(pv, beta, 1.0, z));
+      rz = rz_new;
+      alpha_prev = alpha; beta_prev = beta;
+    }
+  }
+  s->cg_iterations = it;
+  if (nt > 0) EST_CHECK(pmg_host_tridiag_extreme_eigenvalues(nt, diag, off, lmin, lmax));
+done:
+#undef EST_CHECK
+  free(diag); free(off);
+  pmg_vector_destroy(r); pmg_vector_destroy(z); pmg_vector_destroy(pv); pmg_vector_destroy(Ap);
+  return rc;
+}
+
+int pmg_chebyshev_estimate(pmg_chebyshev *s)
+{
+  if (s && s->op) PMG_CHECK(pmg_enter(s->op->ctx));
   double lmin = 1.0, lmax = 1.0;
   s->cg_iterations = 0;
-  if (s->eig_cg_n_iterations > 0) {
-    pmg_vector *r = NULL, *z = NULL, *pv = NULL, *Ap = NULL;
-    PMG_CHECK(pmg_vector_create_layout(ctx, l, &r));
-    PMG_CHECK(pmg_vector_create_layout(ctx, l, &z));
-    PMG_CHECK(pmg_vector_create_layout(ctx, l, &pv));
-    PMG_CHECK(pmg_vector_create_layout(ctx, l, &Ap));
-    const int max_it = s->eig_cg_n_iterations;
-    double *diag = (double *)calloc((size_t)max_it + 2, sizeof(double));
-    double *off = (double *)calloc((size_t)max_it + 2, sizeof(double));
-    int nt = 0, it = 0;
-    /* start vector on all stored planes (global index => identical on any rank count) */
-    PMG_CHECK(pmgk_set_mod11(r->d, l->plane * l->z0, l->n_local, ctx->stream));
-    double mean = 0.0, res = 0.0, rz = 0.0;
-    PMG_CHECK(pmg_vector_mean_value(r, &mean));
-    PMG_CHECK(pmgk_set(z->d, -mean, l->n_local, ctx->stream));
-    PMG_CHECK(pmg_vector_add(r, 1.0, z)); /* r = v - mean */
-    PMG_CHECK(pmg_vector_l2_norm(r, &res));
-    if (res > 1e-10) {
-      PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0, r->d, z->d, ctx->stream));
-      PMG_CHECK(pmg_vector_copy(pv, z));
-      PMG_CHECK(pmg_vector_dot(r, z, &rz));
-      double alpha_prev = 0.0, beta_prev = 0.0, eigen_beta_alpha = 0.0;
-      for (;;) {
-        ++it;
-        PMG_CHECK(pmg_laplace_operator_vmult(op, Ap, pv));
-        double pAp = 0.0;
-        PMG_CHECK(pmg_vector_dot(pv, Ap, &pAp));
-        const double alpha = rz / pAp;
-        PMG_CHECK(pmg_vector_add(r, -alpha, Ap));
-        PMG_CHECK(pmg_vector_l2_norm(r, &res));
-        if (it > 1) {
-          diag[nt] = 1.0 / alpha_prev + eigen_beta_alpha;
-          eigen_beta_alpha = beta_prev / alpha_prev;
-          off[nt] = sqrt(beta_prev) / alpha_prev;
-          ++nt;
-        }
-        if (res <= 1e-10 || it >= max_it) break;
-        PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0, r->d, z->d, ctx->stream));
-        double rz_new = 0.0;
-        PMG_CHECK(pmg_vector_dot(r, z, &rz_new));
-        const double beta = rz_new / rz;
-        PMG_CHECK(pmg_vector_sadd(pv, beta, 1.0, z));
-        rz = rz_new;
-        alpha_prev = alpha; beta_prev = beta;
-      }
-    }
-    s->cg_iterations = it;
-    if (nt > 0) PMG_CHECK(pmg_host_tridiag_extreme_eigenvalues(nt, diag, off, &lmin, &lmax));
-    free(diag); free(off);
-    pmg_vector_destroy(r); pmg_vector_destroy(z); pmg_vector_destroy(pv); pmg_vector_destroy(Ap);
-  }
+  /* no estimate run (eig_cg_n_iterations == 0): the configured largest eigenvalue (1) is used as it is, like deal.II does;
+     the 1.2 safety factor belongs to an unconverged CG estimate only */
+  const double safety = (s->eig_cg_n_iterations > 0) ? 1.2 : 1.0;
+  if (s->eig_cg_n_iterations > 0) PMG_CHECK(estimate_lanczos(s, &lmin, &lmax));
   int degree = s->degree;
-  PMG_CHECK(pmg_host_chebyshev_parameters(lmin, lmax, s->smoothing_range, s->degree, &s->theta, &s->delta, &degree));
+  PMG_CHECK(chebyshev_parameters(lmin, safety * lmax, s->smoothing_range, s->degree, &s->theta, &s->delta, &degree));
   s->degree = degree;
   s->lambda_min = lmin;
-  s->lambda_max = 1.2 * lmax;
+  s->lambda_max = safety * lmax;
   s->initialized = 1;
   return PMG_OK;
 }
@@ -188,6 +222,7 @@ int pmg_chebyshev_info(pmg_chebyshev *s, double *lambda_min, double *lambda_max,
 int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp, int zero_guess,
                          pmg_vector **result)
 {
+  if (s && s->op) PMG_CHECK(pmg_enter(s->op->ctx));
   if (!s->initialized) PMG_CHECK(pmg_chebyshev_estimate(s));
   pmg_operator *op = s->op;
   pmg_context *ctx = op->ctx;

@@ -108,10 +108,10 @@ static int gather_to_root(pmg_context *ctx, const pmg_vector *dist, pmg_vector *
       int lo, hi;
       pmg_host_partition(l->nz, ctx->n_ranks, r, &lo, &hi);
       const int zlo = lo * l->degree, zhi = (r == ctx->n_ranks - 1) ? l->Nz : hi * l->degree;
-      PMG_NCCL(ncclRecv(full->d + l->plane * zlo, (size_t)(l->plane * (zhi - zlo)), ncclDouble, r, ctx->comm, ctx->stream));
+      PMG_NCCL_IN_GROUP(ncclRecv(full->d + l->plane * zlo, (size_t)(l->plane * (zhi - zlo)), ncclDouble, r, ctx->comm, ctx->stream));
     }
   } else {
-    PMG_NCCL(ncclSend(dist->d + l->plane * (l->z_own_lo - l->z0), (size_t)(l->plane * (l->z_own_hi - l->z_own_lo)), ncclDouble, 0, ctx->comm, ctx->stream));
+    PMG_NCCL_IN_GROUP(ncclSend(dist->d + l->plane * (l->z_own_lo - l->z0), (size_t)(l->plane * (l->z_own_hi - l->z_own_lo)), ncclDouble, 0, ctx->comm, ctx->stream));
   }
   PMG_NCCL(ncclGroupEnd());
   pmg_count_launch(1);
@@ -134,10 +134,10 @@ static int scatter_add_from_root(pmg_context *ctx, const pmg_vector *full, pmg_v
       int lo, hi;
       pmg_host_partition(l->nz, ctx->n_ranks, r, &lo, &hi);
       const int zlo = lo * l->degree, zhi = (r == ctx->n_ranks - 1) ? l->Nz : hi * l->degree;
-      PMG_NCCL(ncclSend(full->d + l->plane * zlo, (size_t)(l->plane * (zhi - zlo)), ncclDouble, r, ctx->comm, ctx->stream));
+      PMG_NCCL_IN_GROUP(ncclSend(full->d + l->plane * zlo, (size_t)(l->plane * (zhi - zlo)), ncclDouble, r, ctx->comm, ctx->stream));
     }
   } else {
-    PMG_NCCL(ncclRecv(tmp, (size_t)n_own, ncclDouble, 0, ctx->comm, ctx->stream));
+    PMG_NCCL_IN_GROUP(ncclRecv(tmp, (size_t)n_own, ncclDouble, 0, ctx->comm, ctx->stream));
   }
   PMG_NCCL(ncclGroupEnd());
   pmg_count_launch(1);
@@ -152,6 +152,7 @@ static int scatter_add_from_root(pmg_context *ctx, const pmg_vector *full, pmg_v
 
 int pmg_transfer_prolongate_and_add(const pmg_transfer *t, pmg_vector *dst_fine, const pmg_vector *src_coarse)
 {
+  if (dst_fine) PMG_CHECK(pmg_enter(dst_fine->ctx));
   PMG_CHECK(check(t, dst_fine, src_coarse));
   pmg_context *ctx = t->ctx;
   if (t->gather_buf) {
@@ -171,6 +172,7 @@ int pmg_transfer_prolongate_and_add(const pmg_transfer *t, pmg_vector *dst_fine,
 
 int pmg_transfer_restrict_and_add(const pmg_transfer *t, pmg_vector *dst_coarse, const pmg_vector *src_fine)
 {
+  if (dst_coarse) PMG_CHECK(pmg_enter(dst_coarse->ctx));
   PMG_CHECK(check(t, src_fine, dst_coarse));
   pmg_context *ctx = t->ctx;
   if (t->gather_buf) {

@@ -12,6 +12,7 @@
  * launch latency that dominates the coarse levels (1..512 cells).
  */
 #include "pmg_internal.h"
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,8 +28,13 @@ struct pmg_vcycle {
   pmg_vector *sol[PMG_MAX_LEVELS], *rhs[PMG_MAX_LEVELS], *tmp[PMG_MAX_LEVELS], *res[PMG_MAX_LEVELS];
   int coarse_top;   /* levels 0 .. coarse_top run as one single-CTA kernel (csrc/pmg_coarse_cycle.h); -1 = none, -2 = undecided */
   int graph_enabled, calls;
-  cudaGraphExec_t graph_exec;
-  const double *graph_dst, *graph_src;
+  int nvtx_open;
+  /* captured cycles, keyed by the (dst, src) pair they were captured for: the CG work vectors and a caller's own vectors
+     alternate without re-capturing; when the cache is full the oldest entry goes (round robin) */
+#define PMG_GRAPH_CACHE 4
+  cudaGraphExec_t graph_exec[PMG_GRAPH_CACHE];
+  const double *graph_dst[PMG_GRAPH_CACHE], *graph_src[PMG_GRAPH_CACHE];
+  int graph_next;
   pmg_vector *host_dst, *host_src;
   double *pinned_in, *pinned_out;
   /* profiling */
@@ -40,8 +46,23 @@ struct pmg_vcycle {
 
 enum { CAT_SMOOTH = 0, CAT_TRANSFER = 1, CAT_HALO = 2, CAT_OTHER = 3 };
 
+/* NVTX ranges (visible to Nsight tools; a no-op without one): one per phase of a level while the cycle is enqueued kernel by
+   kernel -- "pmg L<level> smooth | transfer | residual" -- and one around a replayed graph; CG iterations get their own. */
+static void nvtx_phase(pmg_vcycle *v, int level, int cat)
+{
+  static const char *const names[] = {"smooth", "transfer", "halo", "residual+copy"};
+  char buf[64];
+  if (v->nvtx_open) nvtxRangePop();
+  v->nvtx_open = 0;
+  if (level < 0) return;
+  snprintf(buf, sizeof(buf), "pmg L%d Q%d %s", level, v->op[level]->degree, names[cat < 0 || cat > 3 ? 3 : cat]);
+  nvtxRangePushA(buf);
+  v->nvtx_open = 1;
+}
+
 static int mark(pmg_vcycle *v, int level, int cat)
 {
+  nvtx_phase(v, level, cat);
   if (!v->profiling) return PMG_OK;
   if (v->n_marks >= 4096) return PMG_OK;
   const int i = v->n_marks++;
@@ -92,7 +113,8 @@ int pmg_vcycle_destroy(pmg_vcycle *v)
 {
   if (!v) return PMG_OK;
   cudaStreamSynchronize(v->ctx->stream);
-  if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
+  for (int i = 0; i < PMG_GRAPH_CACHE; ++i)
+    if (v->graph_exec[i]) cudaGraphExecDestroy(v->graph_exec[i]);
   for (int l = 0; l < v->n_levels; ++l) {
     pmg_vector_destroy(v->tmp[l]); pmg_vector_destroy(v->res[l]);
     pmg_vector_destroy(v->sol[l]); pmg_vector_destroy(v->rhs[l]);
@@ -210,6 +232,7 @@ static int ensure_initialized(pmg_vcycle *v)
 
 int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
 {
+  if (v) PMG_CHECK(pmg_enter(v->ctx));
   if (!v || !dst || !src || dst == src) { pmg_set_error("vcycle_vmult: bad arguments"); return PMG_ERR_ARG; }
   const int top = v->n_levels - 1;
   if (!pmg_layout_same(&dst->lay, &v->op[top]->lay) || !pmg_layout_same(&src->lay, &v->op[top]->lay)) {
@@ -219,17 +242,32 @@ int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
   PMG_CHECK(ensure_initialized(v));
   pmg_context *ctx = v->ctx;
   /* dst = 0 (:92) is implied: the cycle starts from a zero guess */
-  if (!v->graph_enabled || v->profiling) return v_cycle(v, top, dst, src, 1);
-  if (v->graph_exec && v->graph_dst == dst->d && v->graph_src == src->d) {
-    PMG_CUDA(cudaGraphLaunch(v->graph_exec, ctx->stream));
-    pmg_count_launch(1);
-    return PMG_OK;
+  if (!v->graph_enabled || v->profiling) {
+    const int rc = v_cycle(v, top, dst, src, 1);
+    nvtx_phase(v, -1, 0);
+    return rc;
   }
-  if (v->calls++ == 0) return v_cycle(v, top, dst, src, 1); /* warm-up: sets kernel attributes outside capture */
-  if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = NULL; }
+  for (int i = 0; i < PMG_GRAPH_CACHE; ++i)
+    if (v->graph_exec[i] && v->graph_dst[i] == dst->d && v->graph_src[i] == src->d) {
+      nvtxRangePushA("pmg V-cycle (graph replay)");
+      const cudaError_t ge = cudaGraphLaunch(v->graph_exec[i], ctx->stream);
+      nvtxRangePop();
+      PMG_CUDA(ge);
+      pmg_count_launch(1);
+      return PMG_OK;
+    }
+  if (v->calls++ == 0) { /* warm-up: sets kernel attributes outside capture */
+    const int rc0 = v_cycle(v, top, dst, src, 1);
+    nvtx_phase(v, -1, 0);
+    return rc0;
+  }
+  const int slot = v->graph_next;
+  v->graph_next = (slot + 1) % PMG_GRAPH_CACHE;
+  if (v->graph_exec[slot]) { cudaGraphExecDestroy(v->graph_exec[slot]); v->graph_exec[slot] = NULL; }
   cudaGraph_t graph = NULL;
   PMG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   const int rc = v_cycle(v, top, dst, src, 1);
+  nvtx_phase(v, -1, 0);
   cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
   if (rc != PMG_OK || ce != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
@@ -237,11 +275,11 @@ int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
     v->graph_enabled = 0; /* fall back to plain stream launches of the same kernels */
     return v_cycle(v, top, dst, src, 1);
   }
-  ce = cudaGraphInstantiate(&v->graph_exec, graph, 0);
+  ce = cudaGraphInstantiate(&v->graph_exec[slot], graph, 0);
   cudaGraphDestroy(graph);
-  if (ce != cudaSuccess) { cudaGetLastError(); v->graph_exec = NULL; v->graph_enabled = 0; return v_cycle(v, top, dst, src, 1); }
-  v->graph_dst = dst->d; v->graph_src = src->d;
-  PMG_CUDA(cudaGraphLaunch(v->graph_exec, ctx->stream));
+  if (ce != cudaSuccess) { cudaGetLastError(); v->graph_exec[slot] = NULL; v->graph_enabled = 0; return v_cycle(v, top, dst, src, 1); }
+  v->graph_dst[slot] = dst->d; v->graph_src[slot] = src->d;
+  PMG_CUDA(cudaGraphLaunch(v->graph_exec[slot], ctx->stream));
   pmg_count_launch(1);
   return PMG_OK;
 }
@@ -297,6 +335,7 @@ int pmg_vcycle_profile(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src, do
 int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_vcycle *precond,
                  int max_it, double tol, int *last_step, double *history, int history_cap)
 {
+  if (A) PMG_CHECK(pmg_enter(A->ctx));
   if (!A || !x || !b || max_it < 0) { pmg_set_error("cg_solve: bad arguments"); return PMG_ERR_ARG; }
   if (!pmg_layout_same(&x->lay, &A->lay) || !pmg_layout_same(&b->lay, &A->lay)) {
     pmg_set_error("cg_solve: vectors are not initialised for the operator");

@@ -7,7 +7,6 @@
 #include <cstring>
 #include <type_traits>
 #include "pmg_apply_sweep.h"
-#include "pmg_apply_sweep_pipe.h"
 
 template <class Tile>
 struct SweepHostExec {
@@ -31,7 +30,8 @@ static void sweep_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
                      const double *dinv_vec, const double *dinv_tab)
 {
   // PL: the pipelined variant (csrc/pmg_apply_sweep_pipe.h): two groups of NT threads each
-  using Tile = std::conditional_t<PL != 0, PmgSweepPipe<P, BX, BY, LZ, NT, US, -1, RL, EG>, PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG, RL, A2, EG>>;
+  static_assert(PL == 0, "the pipelined variant was removed in round 2 (superseded by csrc/pmg_apply_plane.h)");
+  using Tile = PmgSweepTile<P, BX, BY, LZ, NT, US, -1, SG, RL, A2, EG>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -89,10 +89,10 @@ extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, un
                          const double *xold, double *out, double f1, double f2, const double *dinv_vec,
                          const double *dinv_tab)
 {
-  g_reverse = (small_tiles == 3 || small_tiles == 7);
-  if (small_tiles == 9 || small_tiles == 10) {
+  g_reverse = (small_tiles == 3);
+  if (small_tiles == 9) {
 #define PMG_EG_CASE(P, BX, BY, LZ, NT, US, RL) \
-  case P: if (small_tiles == 9) sweep_go<P, BX, BY, LZ, NT, US, 1, RL, 0, 0, 1>(ARGS); else sweep_go<P, BX, BY, LZ, NT, US, 1, RL, 0, 1, 1>(ARGS); return 0;
+  case P: sweep_go<P, BX, BY, LZ, NT, US, 1, RL, 0, 0, 1>(ARGS); return 0;
     switch (degree) {
       PMG_EG_CASE(1, 3, 2, 3, 32, 1, 0)
       PMG_EG_CASE(2, 2, 3, 2, 32, 1, 0)
@@ -104,19 +104,6 @@ extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, un
       PMG_EG_CASE(8, 1, 2, 1, 64, 0, 0)
     }
 #undef PMG_EG_CASE
-    return -3;
-  }
-  if (small_tiles == 6 || small_tiles == 7) {
-    switch (degree) {
-      case 1: sweep_go<1, 3, 2, 3, 32, 1, 1, 0, 0, 1>(ARGS); return 0;
-      case 2: sweep_go<2, 2, 3, 2, 32, 0, 1, 0, 0, 1>(ARGS); return 0;
-      case 3: sweep_go<3, 2, 3, 1, 32, 1, 1, 1, 0, 1>(ARGS); return 0;
-      case 4: sweep_go<4, 3, 2, 1, 64, 1, 1, 1, 0, 1>(ARGS); return 0;
-      case 5: sweep_go<5, 2, 3, 1, 32, 0, 1, 0, 0, 1>(ARGS); return 0;
-      case 6: sweep_go<6, 2, 1, 1, 32, 1, 1, 0, 0, 1>(ARGS); return 0;
-      case 7: sweep_go<7, 1, 2, 1, 32, 1, 1, 1, 0, 1>(ARGS); return 0;
-      case 8: sweep_go<8, 1, 2, 1, 64, 0, 1, 0, 0, 1>(ARGS); return 0;
-    }
     return -3;
   }
   if (small_tiles == 5) {

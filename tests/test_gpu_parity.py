@@ -16,9 +16,7 @@ APPLY_TOL = 1e-12
 HISTORY_TOL = 1e-10
 
 
-# PMG_TEST_PIPE=1 adds the pipelined line-marching kernel (PMG_TILE_VARIANT=4 and 5, csrc/pmg_apply_sweep_pipe.h: experimental,
-# emulator-verified, first GPU run pending) to the kernels every test is run with
-_KERNELS = ["auto", "plane", "sweep", "celltile"] + (["pipe", "pipe_eg"] if os.environ.get("PMG_TEST_PIPE") == "1" else [])
+_KERNELS = ["auto", "plane", "sweep", "celltile"]
 
 
 @pytest.fixture(autouse=True, params=_KERNELS)
@@ -30,7 +28,7 @@ def apply_kernel(request, monkeypatch):
     if request.param == "auto":
         monkeypatch.delenv("PMG_TILE_VARIANT", raising=False)
     else:
-        monkeypatch.setenv("PMG_TILE_VARIANT", {"sweep": "1", "celltile": "2", "pipe": "4", "pipe_eg": "5", "plane": "6"}[request.param])
+        monkeypatch.setenv("PMG_TILE_VARIANT", {"sweep": "1", "celltile": "2", "plane": "6"}[request.param])
     return request.param
 
 

@@ -274,37 +274,6 @@ def test_emulated_sweep_with_rolled_cell_loops(p, small, emu, oracle):
         assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.7, small=small, faces=faces), ref) < 1e-13
 
 
-@pytest.mark.parametrize("p", range(1, 9))
-@pytest.mark.parametrize("small", [6, 7, 9, 10])
-def test_emulated_pipelined_sweep(p, small, emu, oracle):
-    """csrc/pmg_apply_sweep_pipe.h: the y/x sweeps of step s and the z sweep + epilogue of step s - 1 run on two thread groups of
-    one CTA (three u staging buffers, two C/D pairs, two b / x_old boxes).  Enough layers for every buffer to be reused several
-    times; chunked and unchunked; all epilogues incl. x_old overwritten in place; a slab with ghost planes.  small = 7 runs the
-    threads in descending order, i.e. the z-sweep group of a tick before its y/x group.  small = 9 / 10: EG = 1 (b and x_old read
-    from global memory by the z sweep instead of being staged in shared memory) for the plain / the pipelined kernel."""
-    n = (5, 4, 9) if p < 3 else (4, 3, 7) if p < 5 else (3, 2, 5)
-    for faces in (0x3F, 0x15):
-        mf = oracle.MatrixFree(3, p, n, faces=faces)
-        u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (91, 92, 93))
-        Au, dinv = mf.vmult(u), mf.compute_diagonal()
-        for chunks in (1, 2):
-            out = emu_apply(emu, p, n, u, small=small, chunks=chunks, faces=faces)
-            assert not np.isnan(out).any() and rel_l2(out, Au) < 1e-13
-        assert rel_l2(emu_apply(emu, p, n, u, mode=1, b=b, small=small, faces=faces), b - Au) < 1e-13
-        assert rel_l2(emu_apply(emu, p, n, u, mode=2, b=b, f2=0.7, small=small, chunks=2, faces=faces), u + 0.7 * dinv * (b - Au)) < 1e-13
-        ref = u + 0.3 * (u - xo) + 0.7 * dinv * (b - Au)
-        assert rel_l2(emu_apply(emu, p, n, u, mode=3, b=b, xold=xo, f1=0.3, f2=0.7, small=small, faces=faces), ref) < 1e-13
-        x2 = xo.copy()
-        emu_apply(emu, p, n, u, mode=3, b=b, xold=x2, f1=0.3, f2=0.7, small=small, chunks=3, faces=faces, out=x2)
-        assert rel_l2(x2, ref) < 1e-13
-    mf = oracle.MatrixFree(3, p, n)
-    u = splitmix_src(mf.n_dofs, salt=94)
-    ref, plane = mf.vmult(u), mf.nd[0] * mf.nd[1]
-    lo, hi = 2, n[2] - 1
-    z0, nzl, _, _, zol, zoh = sl = slab_of(p, n, lo, hi)
-    ol = emu_apply(emu, p, n, u[z0 * plane:(z0 + nzl) * plane].copy(), slab=sl, chunks=2, small=small)
-    assert rel_l2(ol[(zol - z0) * plane:(zoh - z0) * plane], ref[zol * plane:zoh * plane]) < 1e-13
-    assert np.isnan(ol[:(zol - z0) * plane]).all() and np.isnan(ol[(zoh - z0) * plane:]).all()
 
 
 # ---- variable-coefficient tile program (csrc/pmg_apply_var.h) under the host emulator ---------------------
