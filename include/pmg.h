@@ -46,7 +46,7 @@ extern "C" {
 #define PMG_ERR_NOT_CONVERGED (-6)/* SolverControl::NoConvergence */
 #define PMG_ERR_STATE (-7)        /* e.g. diagonal requested before compute_diagonal (reference: ExcNotInitialized) */
 
-#define PMG_MAX_DEGREE 8          /* reference dispatcher max_degree = 9 (portable_laplace_operator_base.h:65) */
+#define PMG_MAX_DEGREE 9          /* = the reference dispatcher's max_degree (portable_laplace_operator_base.h:65) */
 #define PMG_ALL_FACES 0x3Fu
 #define PMG_INVALID_DEGREE (-1)   /* numbers::invalid_unsigned_int for the Chebyshev degree */
 

@@ -171,6 +171,7 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
     case 6: PMG_LAUNCH(6, 5, 5, 1);
     case 7: PMG_LAUNCH(7, 4, 5, 1);
     case 8: PMG_LAUNCH(8, 4, 4, 1);
+    case 9: PMG_LAUNCH(9, 3, 3, 1);
     default: return PMG_ERR_UNSUPPORTED;
   }
 #undef PMG_LAUNCH

@@ -208,6 +208,7 @@ extern "C" int pmgk_var_fill_coef(const pmgk_level *lv, int kind, const double *
     case 6: return fill_coef<6>(lv, gq, gw, coef, (cudaStream_t)stream);
     case 7: return fill_coef<7>(lv, gq, gw, coef, (cudaStream_t)stream);
     case 8: return fill_coef<8>(lv, gq, gw, coef, (cudaStream_t)stream);
+    case 9: return fill_coef<9>(lv, gq, gw, coef, (cudaStream_t)stream);
     default: return PMG_ERR_UNSUPPORTED;
   }
 }
@@ -224,6 +225,7 @@ extern "C" int pmgk_var_fill_dinv(const pmgk_level *lv, const double *S2, const 
     case 6: return fill_dinv<6>(lv, S2, G2, dinv, (cudaStream_t)stream);
     case 7: return fill_dinv<7>(lv, S2, G2, dinv, (cudaStream_t)stream);
     case 8: return fill_dinv<8>(lv, S2, G2, dinv, (cudaStream_t)stream);
+    case 9: return fill_dinv<9>(lv, S2, G2, dinv, (cudaStream_t)stream);
     default: return PMG_ERR_UNSUPPORTED;
   }
 }

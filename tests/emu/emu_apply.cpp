@@ -77,6 +77,7 @@ extern "C" int emu_apply(int degree, int small_tiles, int nx, int ny, int nz, un
       case 6: go<6, 2, 1>(ARGS); return 0;
       case 7: go<7, 1, 2>(ARGS); return 0;
       case 8: go<8, 2, 2>(ARGS); return 0;
+      case 9: go<9, 2, 1>(ARGS); return 0;
     }
     return -3;
   }
@@ -89,6 +90,7 @@ extern "C" int emu_apply(int degree, int small_tiles, int nx, int ny, int nz, un
     case 6: go<6, 5, 5>(ARGS); return 0;
     case 7: go<7, 4, 5>(ARGS); return 0;
     case 8: go<8, 4, 4>(ARGS); return 0;
+    case 9: go<9, 3, 3>(ARGS); return 0;
   }
   return -3;
 }

@@ -90,6 +90,7 @@ extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, un
       case 6: plane_go<6, 2, 1, 32>(ARGS); return 0;
       case 7: plane_go<7, 1, 2, 32>(ARGS); return 0;
       case 8: plane_go<8, 2, 2, 64>(ARGS); return 0;
+      case 9: plane_go<9, 1, 2, 64>(ARGS); return 0;
     }
     return -3;
   }

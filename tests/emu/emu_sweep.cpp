@@ -155,6 +155,7 @@ extern "C" int emu_sweep(int degree, int small_tiles, int nx, int ny, int nz, un
       case 6: sweep_go<6, 2, 1, 1, 32>(ARGS); return 0;
       case 7: sweep_go<7, 1, 2, 2, 32>(ARGS); return 0;
       case 8: sweep_go<8, 2, 2, 1, 64>(ARGS); return 0;
+      case 9: sweep_go<9, 1, 2, 1, 64>(ARGS); return 0;
     }
     return -3;
   }

@@ -101,6 +101,7 @@ extern "C" int emu_var(int degree, int small_tiles, int nx, int ny, int nz, unsi
       case 6: go<6, 2, 1>(a); return 0;
       case 7: go<7, 1, 2>(a); return 0;
       case 8: go<8, 2, 2>(a); return 0;
+      case 9: go<9, 1, 2>(a); return 0;
     }
     return -3;
   }

@@ -12,7 +12,7 @@ from helpers import rel_l2, splitmix_src
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_2d_vmult_diagonal_and_fused_steps(p, pmg, ctx, oracle):
     n = (37, 21) if p < 4 else (9, 14)
     mf = oracle.MatrixFree(2, p, n)

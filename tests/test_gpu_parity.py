@@ -45,7 +45,7 @@ def _oracle_hierarchy(oracle, levels, **kw):
     return mfs, trs, oracle.VCycle(mfs, trs, **kw)
 
 
-@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_vmult_matches_oracle(p, pmg, ctx, oracle):
     n = {1: (17, 16, 18), 2: (13, 14, 9), 3: (11, 10, 7), 4: (9, 8, 5)}.get(p, (5, 6, 4))
     mf = oracle.MatrixFree(3, p, n)

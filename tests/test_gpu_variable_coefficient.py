@@ -9,7 +9,7 @@ from helpers import hierarchy_levels, rel_l2, splitmix_src
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_variable_coefficient_vmult_diagonal_and_fused_steps(p, pmg, ctx, oracle):
     n = {1: (17, 16, 18), 2: (13, 14, 9), 3: (11, 10, 7), 4: (9, 8, 5)}.get(p, (5, 6, 4))
     mf = oracle.MatrixFree(3, p, n, coef="c5")

@@ -59,7 +59,7 @@ def test_product_does_not_reference_the_oracle():
 
 
 # ---- host helpers vs oracle ------------------------------------------------------------------------
-@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("p", range(1, 10))
 def test_fastdiag_tables(p, pmg, oracle):
     S, lam = pmg.host_fastdiag_tables(p)
     M, K = pmg.host_pencil(p)
@@ -72,10 +72,10 @@ def test_fastdiag_tables(p, pmg, oracle):
     assert np.linalg.cond(S) < 40  # well conditioned change of basis: no accuracy lost
 
 
-@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("p", range(1, 10))
 def test_prolongation_matrices(p, pmg, oracle):
     assert np.abs(pmg.host_prolongation_1d(0, p) - oracle.h_prolongation_1d(p)).max() < 1e-14
-    for pf in range(p + 1, 9):
+    for pf in range(p + 1, 10):
         assert np.abs(pmg.host_prolongation_1d(1, p, pf) - oracle.p_prolongation_1d(p, pf)).max() < 1e-14
 
 
@@ -150,7 +150,7 @@ def slab_of(p, n, cz_lo, cz_hi):
     return z0, z_end - z0, cz_lo, cz_hi, cz_lo * p, (Nz if cz_hi == n[2] else cz_hi * p)
 
 
-@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("p", range(1, 10))
 @pytest.mark.parametrize("small,chunks", [(1, 1), (1, 3), (0, 2)])
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_emulated_apply_matches_oracle(p, small, chunks, kernel, emu, oracle):
@@ -291,7 +291,7 @@ def emu_var(emu, p, n, u, mode=0, b=None, xold=None, f1=0.0, f2=0.0, small=1, ch
     return (out, dv) if want_dinv else out
 
 
-@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("p", range(1, 10))
 @pytest.mark.parametrize("small,chunks", [(1, 1), (1, 3), (0, 2)])
 def test_emulated_variable_coefficient_apply_matches_oracle(p, small, chunks, emu, oracle):
     n = (5, 4, 3) if p < 5 else (3, 2, 3)
@@ -342,7 +342,7 @@ def test_emulated_variable_coefficient_slabs(p, splits, emu, oracle):
 
 
 # ---- the 2-D kernels' per-DoF functions (csrc/pmg_dim2.h) under the host emulator ----------------------------------
-@pytest.mark.parametrize("p", range(1, 9))
+@pytest.mark.parametrize("p", range(1, 10))
 @pytest.mark.parametrize("faces", [0xF, 0x5, 0x0])
 def test_emulated_2d_apply_and_epilogues(p, faces, emu, oracle):
     n = (5, 3) if p < 5 else (3, 2)
