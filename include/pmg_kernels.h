@@ -116,6 +116,16 @@ int pmgk_restrict_and_add(int kind, const pmgk_level *coarse, const pmgk_level *
                           double *dst_coarse, const double *src_fine, double *scratch, void *stream);
 int64_t pmgk_restrict_scratch_doubles(int kind, const pmgk_level *coarse, const pmgk_level *fine);
 
+/* ghost planes of a z-slab over NVLink peer memory (csrc/pmg_halo.cu): this rank's boundary planes are stored into the
+   neighbours' ghost planes -- peer_lower[dst_in_lower + i] = mine[src_to_lower + i], i < n_to_lower (NULL peer: no neighbour),
+   likewise upper -- ordered by flags; mailbox: this rank's six 64-bit flag words (device, zero-initialised),
+   mailbox_lower / _upper: the neighbours' mailboxes as mapped here; need_ready: first wait until the neighbours no longer read the
+   ghost planes that are about to be overwritten (required when the previous exchange was on the same vector).  When the kernel
+   ends this rank's ghost planes are current. */
+int pmgk_halo_push(const double *mine, double *peer_lower, double *peer_upper, int64_t n_to_lower, int64_t src_to_lower,
+                   int64_t dst_in_lower, int64_t n_to_upper, int64_t src_to_upper, int64_t dst_in_upper, void *mailbox,
+                   void *mailbox_lower, void *mailbox_upper, int need_ready, void *stream);
+
 /* device properties the host layer needs */
 int pmgk_device_sm_count(void);
 /* FP64 microbenchmarks (roofline denominators): returns TFLOP/s */

@@ -99,7 +99,7 @@ PMG_SWEEP_DECL(0) PMG_SWEEP_DECL(1) PMG_SWEEP_DECL(2) PMG_SWEEP_DECL(3)
 // plane-per-step kernel, one translation unit per epilogue mode (4 = CHEB_STEP without x_old): csrc/pmg_apply_plane_m<mode>.cu
 #define PMG_PLANE_DECL(m) \
   int pmg_plane_dispatch_m##m(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, \
-                              double f2, cudaStream_t s, int *geom);
+                              double f2, cudaStream_t s, int *geom, int part);
 PMG_PLANE_DECL(0) PMG_PLANE_DECL(1) PMG_PLANE_DECL(2) PMG_PLANE_DECL(3) PMG_PLANE_DECL(4)
 #undef PMG_PLANE_DECL
 #define PMG_PLANE_MAX_DEGREE 6
@@ -116,9 +116,10 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
                     double *out, double f1, double f2, cudaStream_t s, int *geom, int part = PMGK_PART_ALL)
 {
   const int64_t n_loc = (int64_t)lv->Nx * lv->Ny * lv->nzl;
-  const bool sweep_kernel = lv->dim == 3 && !lv->coef && (part != PMGK_PART_ALL || lv->degree > PMG_PLANE_MAX_DEGREE || lv->tile_variant != 0) &&
-                            (lv->tile_variant == 1 || lv->tile_variant == 6 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
-  if (part != PMGK_PART_ALL && !sweep_kernel) return PMG_ERR_UNSUPPORTED; /* only the line-marching kernel launches in parts */
+  /* the plane-per-step and the line-marching kernel launch in parts (their launches are cut into z-chunks) */
+  const bool chunked_kernel = lv->dim == 3 && !lv->coef &&
+                              (lv->tile_variant == 1 || lv->tile_variant == 6 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
+  if (part != PMGK_PART_ALL && !chunked_kernel) return PMG_ERR_UNSUPPORTED;
   if (lv->dim == 2) return pmg_dim2_apply(lv, mode, u, b, xold, out, f1, f2, s, geom);
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
   if (lv->coef) return pmg_var_dispatch(lv, mode, u, b, xold, out, f1, f2, s, geom);
@@ -132,13 +133,13 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
   /* round 2: the plane-per-step kernel (csrc/pmg_apply_plane.h) takes the large levels of degrees 1..6 (measured at 100 M DoFs,
      apply / fused step in GDoF/s against the line-marching kernel: Q2 170 / 123 : 112 / 80, Q4 140 / 98 : 122 / 87);
      tile_variant 6 forces it, 1 forces the line-marching kernel */
-  if (part == PMGK_PART_ALL && lv->degree <= PMG_PLANE_MAX_DEGREE && (lv->tile_variant == 6 || (lv->tile_variant == 0 && !small_level))) {
+  if (lv->degree <= PMG_PLANE_MAX_DEGREE && (lv->tile_variant == 6 || (lv->tile_variant == 0 && !small_level))) {
     switch (mode) {
-      case PMGK_APPLY: return pmg_plane_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom);
-      case PMGK_RESIDUAL: return pmg_plane_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom);
-      case PMGK_CHEB_FIRST: return pmg_plane_dispatch_m2(lv, u, b, xold, out, f1, f2, s, geom);
-      case PMGK_CHEB_STEP: return xold ? pmg_plane_dispatch_m3(lv, u, b, xold, out, f1, f2, s, geom)
-                                       : pmg_plane_dispatch_m4(lv, u, b, xold, out, f1, f2, s, geom);
+      case PMGK_APPLY: return pmg_plane_dispatch_m0(lv, u, b, xold, out, f1, f2, s, geom, part);
+      case PMGK_RESIDUAL: return pmg_plane_dispatch_m1(lv, u, b, xold, out, f1, f2, s, geom, part);
+      case PMGK_CHEB_FIRST: return pmg_plane_dispatch_m2(lv, u, b, xold, out, f1, f2, s, geom, part);
+      case PMGK_CHEB_STEP: return xold ? pmg_plane_dispatch_m3(lv, u, b, xold, out, f1, f2, s, geom, part)
+                                       : pmg_plane_dispatch_m4(lv, u, b, xold, out, f1, f2, s, geom, part);
       default: return PMG_ERR_ARG;
     }
   }

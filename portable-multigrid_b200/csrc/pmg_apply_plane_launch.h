@@ -16,7 +16,7 @@ struct PmgPlaneDeviceExec {
 
 template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM>
 __global__ void __launch_bounds__(NT, MINB)
-pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p)
+pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
   using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ>;
   extern __shared__ __align__(128) double pmg_plane_smem[];
@@ -24,7 +24,9 @@ pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p)
   const int b = blockIdx.x;
   const int tile_x = b % p.tiles_x;
   const int tile_y = (b / p.tiles_x) % p.tiles_y;
-  const int chunk = b / (p.tiles_x * p.tiles_y);
+  // the launch's CTAs work on z-chunks chunk_first + i * chunk_stride (all chunks: 0, 1; the two chunks that read the slab's
+  // ghost planes: 0, n_chunks - 1; the others: 1, 1)
+  const int chunk = chunk_first + (b / (p.tiles_x * p.tiles_y)) * chunk_stride;
   Tile::run(p, ex, pmg_plane_smem, tile_x, tile_y, chunk);
 }
 
@@ -54,7 +56,7 @@ inline void choose_plane_chunks(int tiles, int layers, int slots, int degree, in
 
 template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM>
 int launch_plane(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
-                 cudaStream_t stream, int *geom)
+                 cudaStream_t stream, int *geom, int part)
 {
   using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ>;
   auto kernel = pmg_plane_kernel<P, BX, BY, NT, MINB, UZ, FM>;
@@ -86,11 +88,19 @@ int launch_plane(const pmgk_level *lv, const double *u, const double *b, const d
   pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
   p.mode = (FM == 4) ? PMG_MODE_CHEB_STEP : FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
-  const int grid = p.tiles_x * p.tiles_y * p.n_chunks;
+  // a launch in parts (halo exchange overlapped with the chunks that read no ghost plane, host/pmg_operator.c): the first and
+  // the last chunk read the slab's ghost planes, the others run while those are in flight
+  int chunk_first = 0, chunk_stride = 1, chunk_count = p.n_chunks;
+  if (part != PMGK_PART_ALL) {
+    if (p.n_chunks < 3) return PMG_ERR_UNSUPPORTED;
+    if (part == PMGK_PART_INTERIOR) { chunk_first = 1; chunk_count = p.n_chunks - 2; }
+    else { chunk_stride = p.n_chunks - 1; chunk_count = 2; }
+  }
+  const int grid = p.tiles_x * p.tiles_y * chunk_count;
   if (geom) { geom[0] = grid; geom[1] = NT; geom[2] = smem_bytes; geom[3] = p.n_chunks; return 0; }
   /* the kernel indexes inside a dof plane with 32-bit element offsets (planes themselves are 64-bit offsets apart) */
   if ((int64_t)lv->Nx * lv->Ny * 4 >= (int64_t)1 << 31) return PMG_ERR_UNSUPPORTED;
-  kernel<<<grid, NT, smem_bytes, stream>>>(p);
+  kernel<<<grid, NT, smem_bytes, stream>>>(p, chunk_first, chunk_stride);
   PMG_CUDA_CHECK(cudaGetLastError());
   pmg_count_launch(1);
   return 0;
@@ -102,11 +112,11 @@ int launch_plane(const pmgk_level *lv, const double *u, const double *b, const d
 #define PMG_PLANE_CAT(a, b) PMG_PLANE_CAT2(a, b)
 
 int PMG_PLANE_CAT(pmg_plane_dispatch_m, PMG_PLANE_TU_MODE)(const pmgk_level *lv, const double *u, const double *b, const double *xold,
-                                                           double *out, double f1, double f2, cudaStream_t s, int *geom)
+                                                           double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
   switch (lv->degree) {
 #define PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ) \
-  case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom);
+  case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE>(lv, u, b, xold, out, f1, f2, s, geom, part);
 #if PMG_PLANE_TU_MODE == 0
 #define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ)
 #define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ)

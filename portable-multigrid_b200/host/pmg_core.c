@@ -85,6 +85,7 @@ static int context_init(pmg_context *ctx, const void *nccl_id)
     memcpy(&id, nccl_id, sizeof(id));
     PMG_NCCL(ncclCommInitRank(&ctx->comm, n_ranks, id, rank));
     ctx->has_comm = 1;
+    PMG_CHECK(pmg_p2p_init(ctx)); /* ghost planes over NVLink peer memory when CUDA IPC works on every rank (pmg_p2p.c) */
     /* PMG_HALO_OVERLAP=1: halo exchange on its own stream / communicator, overlapped with the interior z-chunks of the apply
        (pmg_operator.c).  OFF by default: measured on 2 B200s (profiles/r01_halo_overlap_2gpu.txt) the split launch is slower
        -- fused step 0.321 against 0.271 ms, V-cycle 9.52 against 7.93 ms: the apply kernel fills every SM, so the NCCL kernel
@@ -92,7 +93,10 @@ static int context_init(pmg_context *ctx, const void *nccl_id)
     const char *ov = getenv("PMG_HALO_OVERLAP");
     if (ov && atoi(ov) != 0) {
       PMG_NCCL(ncclCommSplit(ctx->comm, 0, rank, &ctx->halo_comm, NULL));
-      PMG_CUDA(cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking));
+      /* highest priority: the exchange's kernels take the first CTA slots the running apply frees */
+      int prio_lo = 0, prio_hi = 0;
+      PMG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      PMG_CUDA(cudaStreamCreateWithPriority(&ctx->halo_stream, cudaStreamNonBlocking, prio_hi));
       PMG_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
       PMG_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
       ctx->overlap = 1;
@@ -128,6 +132,7 @@ int pmg_context_destroy(pmg_context *ctx)
     cudaEventDestroy(ctx->ev_ready); cudaEventDestroy(ctx->ev_halo);
     cudaStreamDestroy(ctx->halo_stream);
   }
+  if (ctx->has_comm) pmg_p2p_shutdown(ctx);
   if (ctx->has_comm) ncclCommDestroy(ctx->comm);
   cudaFree(ctx->work); cudaFree(ctx->scalars); cudaFreeHost(ctx->h_scalars);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -233,14 +238,17 @@ int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector
   if (!v) return PMG_ERR_NOMEM;
   v->ctx = ctx; v->lay = *lay;
   if (lay->n_local > 0) {
+    v->d = pmg_p2p_acquire(ctx, lay); /* a released array of this level that the neighbours already have mapped */
+    const int fresh = (v->d == NULL);
     /* + 16 bytes: the apply kernel's bulk row copies fetch whole 16-byte granules (csrc/pmg_apply_sweep.h) */
-    if (cudaMalloc((void **)&v->d, sizeof(double) * ((size_t)lay->n_local + 2)) != cudaSuccess) {
+    if (fresh && cudaMalloc((void **)&v->d, sizeof(double) * ((size_t)lay->n_local + 2)) != cudaSuccess) {
       pmg_set_error("cudaMalloc of %lld doubles failed", (long long)lay->n_local);
       free(v);
       return PMG_ERR_NOMEM;
     }
-    const int rc = pmgk_set(v->d, 0.0, lay->n_local, ctx->stream);
-    if (rc) { cudaFree(v->d); free(v); return rc; }
+    int rc = pmgk_set(v->d, 0.0, lay->n_local, ctx->stream);
+    if (!rc && fresh) rc = pmg_p2p_register(ctx, lay, v->d); /* collective: handle exchange with the slab neighbours */
+    if (rc) { if (!pmg_p2p_release(ctx, v->d)) cudaFree(v->d); free(v); return rc; }
   }
   *out = v;
   return PMG_OK;
@@ -250,7 +258,7 @@ int pmg_vector_destroy(pmg_vector *v)
 {
   if (!v) return PMG_OK;
   cudaStreamSynchronize(v->ctx->stream);
-  if (!v->borrowed) cudaFree(v->d);
+  if (!v->borrowed && !pmg_p2p_release(v->ctx, v->d)) cudaFree(v->d);
   free(v);
   return PMG_OK;
 }
@@ -400,6 +408,13 @@ int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d)
 int pmg_halo_update_on(pmg_context *ctx, const pmg_layout *lay, double *d, ncclComm_t comm, cudaStream_t stream)
 {
   if (!ctx->has_comm || lay->gathered || !lay->active) return PMG_OK;
+  {
+    /* registered vectors: one push kernel over NVLink peer memory (csrc/pmg_halo.cu); anything else (wrapped arrays, boxes
+       without CUDA IPC): the NCCL send / receive group below */
+    int done = 0;
+    PMG_CHECK(pmg_p2p_halo(ctx, lay, d, stream, &done));
+    if (done) return PMG_OK;
+  }
   const int p = lay->degree;
   const int64_t plane = lay->plane;
   PMG_NCCL(ncclGroupStart());

@@ -65,6 +65,24 @@ void pmg_fe_diag_1d(int p, double *Md, double *Kd);
 void pmg_fe_dinv_table(int p, const double h[3], int dim, double *tab);
 void pmg_fe_shape_tables(int p, double *Sq, double *Dco, double *G, double *gq, double *gw);
 
+/* peer mapping of the slab neighbours' vectors (pmg_p2p.c) */
+#define PMG_P2P_MAX_REG 512
+typedef struct pmg_p2p_reg {
+  double *base;                       /* this rank's array */
+  const double *peer_lower, *peer_upper; /* the neighbours' arrays of the same vector, mapped here */
+  int lower_z0, upper_z0;             /* their first stored dof plane */
+  int key[4];                         /* the level the array was made for: Nx, Ny, Nz, degree (identical on every rank) */
+  int in_use;                         /* 0: released by its vector, kept (mapped on the neighbours) for the next vector of that level */
+} pmg_p2p_reg;
+typedef struct pmg_p2p {
+  int enabled;
+  void *msg_dev;                      /* device scratch of the handle exchange */
+  uint64_t *mailbox, *mb_lower, *mb_upper;
+  pmg_p2p_reg reg[PMG_P2P_MAX_REG];
+  int n_reg;
+  const double *last_base;            /* the array of the previous exchange (NULL: unknown) */
+} pmg_p2p;
+
 struct pmg_context {
   int device;
   int rank, n_ranks;
@@ -81,7 +99,9 @@ struct pmg_context {
   double *scalars;   /* device: small scalar slots */
   double *h_scalars; /* pinned host mirror */
   int sm_count;
+  pmg_p2p p2p;
 };
+
 
 /* one level's decomposition: z-slabs of cell layers, or everything on rank 0 */
 typedef struct pmg_layout {
@@ -97,6 +117,15 @@ typedef struct pmg_layout {
   int64_t n_local;       /* nzl*plane */
   int64_t n_global;
 } pmg_layout;
+
+/* pmg_p2p.c */
+int pmg_p2p_init(pmg_context *ctx);
+void pmg_p2p_shutdown(pmg_context *ctx);
+int pmg_p2p_register(pmg_context *ctx, const pmg_layout *lay, double *d);
+double *pmg_p2p_acquire(pmg_context *ctx, const pmg_layout *lay);
+int pmg_p2p_release(pmg_context *ctx, double *d);
+int pmg_p2p_halo(pmg_context *ctx, const pmg_layout *lay, double *d, cudaStream_t stream, int *done);
+void pmg_p2p_forget(pmg_context *ctx);
 
 struct pmg_vector {
   pmg_context *ctx;

@@ -241,6 +241,7 @@ int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
   }
   PMG_CHECK(ensure_initialized(v));
   pmg_context *ctx = v->ctx;
+  pmg_p2p_forget(ctx); /* a captured cycle's first exchange must not rely on what preceded the capture */
   /* dst = 0 (:92) is implied: the cycle starts from a zero guess */
   if (!v->graph_enabled || v->profiling) {
     const int rc = v_cycle(v, top, dst, src, 1);
@@ -252,6 +253,7 @@ int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
       nvtxRangePushA("pmg V-cycle (graph replay)");
       const cudaError_t ge = cudaGraphLaunch(v->graph_exec[i], ctx->stream);
       nvtxRangePop();
+      pmg_p2p_forget(ctx);
       PMG_CUDA(ge);
       pmg_count_launch(1);
       return PMG_OK;
@@ -279,6 +281,7 @@ int pmg_vcycle_vmult(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src)
   cudaGraphDestroy(graph);
   if (ce != cudaSuccess) { cudaGetLastError(); v->graph_exec[slot] = NULL; v->graph_enabled = 0; return v_cycle(v, top, dst, src, 1); }
   v->graph_dst[slot] = dst->d; v->graph_src[slot] = src->d;
+  pmg_p2p_forget(ctx);
   PMG_CUDA(cudaGraphLaunch(v->graph_exec[slot], ctx->stream));
   pmg_count_launch(1);
   return PMG_OK;

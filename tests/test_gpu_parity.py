@@ -199,7 +199,7 @@ def test_transfer_rejects_incompatible_levels(pmg, ctx):
     with pytest.raises(pmg.PmgError):
         pmg.PolynomialTransfer(a, a)
     with pytest.raises(pmg.PmgError):
-        pmg.LaplaceOperator(ctx, 9, 4)  # outside the compiled degree range
+        pmg.LaplaceOperator(ctx, 10, 4)  # outside the compiled degree range (1..9, the reference dispatcher's max_degree)
 
 
 @pytest.mark.parametrize("p,n,deg", [(2, (6, 5, 4), 5), (3, (4, 4, 4), 3), (4, (3, 4, 3), 5), (1, (8, 8, 8), 1)])
