@@ -393,22 +393,39 @@ def main():
 
     # BASELINE configs[2] point of this degree (standalone apply on a ~100 M-DoF cube, SURVEY 8 "C3"): the same operator call on
     # n = round(464 / p) cells per direction.  Last GPU work of the run and never a dependency of the line above.
-    apply_c3 = None
+    apply_c3, apply_c3_sweep = None, None
     if world == 1 and args.config == "c2" and not coefficient:
-        try:
-            n3 = int(round(464.0 / p))
-            big = G.LaplaceOperator(ctx, p, n3)
-            ub, zb = big.initialize_dof_vector(), big.initialize_dof_vector()
-            ub.set(1.0)
-            for _ in range(3):
-                big.vmult(zb, ub)
-            ms_big = timed(lambda: big.vmult(zb, ub), 10)
-            nb = int(big.m())
-            apply_c3 = {"degree": p, "cells_per_dir": n3, "n_dofs": nb, "ms": ms_big, "gdofs": nb / (ms_big * 1e-3) / 1e9,
-                        "hbm_frac": 16.0 * nb / (ms_big * 1e-3) / 1e9 / peak}
-            del ub, zb, big
-        except Exception as e:
-            apply_c3 = {"error": repr(e)}
+        # BASELINE configs[2]: the degree 1..9 sweep of the standalone apply at ~100 M DoFs, with both rooflines per degree --
+        # HBM (16 B/DoF at the measured copy bandwidth) and FP64 (the 7 one-dimensional band-matrix sweeps of p + 2 FMAs per
+        # DoF at the measured DFMA rate) -- and the degree where the FP64 roof drops below the HBM roof (the "crossover").
+        fma_peak = mb["fp64_fma_tflops"] if mb else None
+        sweep = []
+        for q in range(1, 10):
+            try:
+                n3 = int(round(464.0 / q))
+                big = G.LaplaceOperator(ctx, q, n3)
+                ub, zb = big.initialize_dof_vector(), big.initialize_dof_vector()
+                ub.set(1.0)
+                for _ in range(3):
+                    big.vmult(zb, ub)
+                ms_big = timed(lambda: big.vmult(zb, ub), 5)
+                nb = int(big.m())
+                gd = nb / (ms_big * 1e-3) / 1e9
+                ent = {"degree": q, "cells_per_dir": n3, "n_dofs": nb, "ms": ms_big, "gdofs": gd, "hbm_frac": 16.0 * gd / peak,
+                       "kernel": "pmg_plane_kernel" if q <= 6 else "pmg_sweep_kernel", "hbm_roof_gdofs": peak / 16.0}
+                if fma_peak:
+                    fma_per_dof = 7.0 * (q + 2)
+                    ent["fp64_roof_gdofs"] = fma_peak * 1e3 / (2.0 * fma_per_dof)
+                    ent["fp64_frac"] = gd / ent["fp64_roof_gdofs"]
+                    ent["binding_roof"] = "hbm" if ent["hbm_roof_gdofs"] <= ent["fp64_roof_gdofs"] else "fp64"
+                sweep.append(ent)
+                del ub, zb, big
+            except Exception as e:
+                sweep.append({"degree": q, "error": repr(e)})
+        cross = [e["degree"] for e in sweep if e.get("binding_roof") == "fp64"]
+        apply_c3_sweep = {"points": sweep, "fp64_fma_per_dof": "7 (p + 2)", "crossover_degree": min(cross) if cross else None,
+                          "note": "from crossover_degree on the FP64 roof of the formulation is below the HBM roof; DMMA has the same peak as DFMA on B200 (fp64 block)"}
+        apply_c3 = next((e for e in sweep if e.get("degree") == p and "gdofs" in e), None)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -417,7 +434,7 @@ def main():
                    "parallelism": "z-slabs x%d" % world, "cuda_graph": True},
         "apply_gdofs": n_dofs / (ms_apply * 1e-3) / 1e9, "apply_ms": ms_apply,
         "apply_hbm_frac": 16.0 * n_local / (ms_apply * 1e-3) / 1e9 / peak,
-        "apply_c3": apply_c3,
+        "apply_c3": apply_c3, "apply_c3_sweep": apply_c3_sweep,
         "cg_solve": cg,
         "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
         "clocks": clocks,

@@ -366,6 +366,17 @@ static int fetch_scalar(pmg_context *ctx, int slot, double *result)
   return PMG_OK;
 }
 
+/* x . y into device scalar `slot` of the context (summed over the ranks), no host round trip: CG keeps its scalars on the
+   device and reads back one number per iteration (the residual norm it has to compare with the tolerance) */
+int pmg_vector_dot_device(const pmg_vector *x, const pmg_vector *y, int slot)
+{
+  if (!x || !y || slot < 0 || slot >= 56) return PMG_ERR_ARG;
+  pmg_context *ctx = x->ctx;
+  if (x->lay.active) PMG_CHECK(pmgk_dot(owned_ptr(x), owned_ptr(y), owned_n(x), ctx->scalars + slot, ctx->work, ctx->stream));
+  else PMG_CUDA(cudaMemsetAsync(ctx->scalars + slot, 0, sizeof(double), ctx->stream));
+  return pmg_allreduce_sum(ctx, ctx->scalars + slot, 1);
+}
+
 int pmg_vector_dot(const pmg_vector *x, const pmg_vector *y, double *result)
 {
   if (x) PMG_CHECK(pmg_enter(x->ctx));

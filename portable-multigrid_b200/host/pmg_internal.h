@@ -171,6 +171,7 @@ int pmg_vector_create_layout(pmg_context *ctx, const pmg_layout *lay, pmg_vector
 int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d);
 int pmg_halo_update_on(pmg_context *ctx, const pmg_layout *lay, double *d, ncclComm_t comm, cudaStream_t stream);
 int pmg_allreduce_sum(pmg_context *ctx, double *dev_scalar, int count);
+int pmg_vector_dot_device(const pmg_vector *x, const pmg_vector *y, int slot);
 /* ghost update of u + fused apply; the exchange overlaps the interior z-chunks when the launch splits (pmg_operator.c) */
 int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1, double f2);
 int pmg_chebyshev_estimate(pmg_chebyshev *s);

@@ -353,8 +353,12 @@ int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_
     if (!Aw->cg_ws[i]) PMG_CHECK(pmg_vector_create_layout(ctx, l, &Aw->cg_ws[i]));
   pmg_vector *r = Aw->cg_ws[0], *z = Aw->cg_ws[1], *p = Aw->cg_ws[2], *Ap = Aw->cg_ws[3];
   int it = 0, converged = 0, rc = PMG_OK;
-  double res = 0.0, rz = 0.0;
+  double res = 0.0;
+  /* device scalars of the iteration (slots of ctx->scalars): the host reads back ONE number per iteration, ||r||^2 */
+  enum { S_RR = 0, S_ALPHA = 8, S_RZ = 16, S_PAP = 17, S_RZNEW = 18, S_BETA = 19 };
+  double *S = ctx->scalars;
 #define CG(call) do { rc = (call); if (rc != PMG_OK) goto done; } while (0)
+#define CGC(call) do { if ((call) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; } } while (0)
   /* r = b - A x; convergence check before the first iteration */
   CG(pmg_laplace_operator_residual(A, r, b, x));
   CG(pmg_vector_l2_norm(r, &res));
@@ -363,37 +367,34 @@ int pmg_cg_solve(const pmg_operator *A, pmg_vector *x, const pmg_vector *b, pmg_
   if (!converged) {
     if (precond) CG(pmg_vcycle_vmult(precond, z, r)); else CG(pmg_vector_copy(z, r));
     CG(pmg_vector_copy(p, z));
-    CG(pmg_vector_dot(r, z, &rz));
+    CG(pmg_vector_dot_device(r, z, S_RZ));
   }
   while (!converged && it < max_it) {
     ++it;
     CG(pmg_laplace_operator_vmult(A, Ap, p));
-    double pAp = 0.0;
-    CG(pmg_vector_dot(p, Ap, &pAp));
-    const double alpha = rz / pAp;
-    /* x += alpha p; r -= alpha Ap; ||r||^2 in one pass */
-    ctx->h_scalars[8] = alpha;
+    CG(pmg_vector_dot_device(p, Ap, S_PAP));
+    CG(pmgk_scalar_div(S + S_ALPHA, S + S_RZ, S + S_PAP, ctx->stream)); /* alpha = r.z / p.Ap */
+    /* x += alpha p; r -= alpha Ap; ||r||^2 in one pass over the owned planes (ghost planes are refreshed before they are read) */
     if (l->active) {
-      if (cudaMemcpyAsync(ctx->scalars + 8, ctx->h_scalars + 8, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
-      /* local update over all stored planes, reduction over owned planes only */
       const int64_t lo = l->plane * (l->z_own_lo - l->z0), n_own = l->plane * (l->z_own_hi - l->z_own_lo);
-      CG(pmgk_cg_update_xr(x->d + lo, r->d + lo, p->d + lo, Ap->d + lo, ctx->scalars + 8, n_own, ctx->scalars, ctx->work, ctx->stream));
+      CG(pmgk_cg_update_xr(x->d + lo, r->d + lo, p->d + lo, Ap->d + lo, S + S_ALPHA, n_own, S + S_RR, ctx->work, ctx->stream));
     } else {
-      if (cudaMemsetAsync(ctx->scalars, 0, sizeof(double), ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
+      CGC(cudaMemsetAsync(S + S_RR, 0, sizeof(double), ctx->stream));
     }
-    CG(pmg_allreduce_sum(ctx, ctx->scalars, 1));
-    if (cudaMemcpyAsync(ctx->h_scalars, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = PMG_ERR_CUDA; goto done; }
-    res = sqrt(ctx->h_scalars[0]);
+    CG(pmg_allreduce_sum(ctx, S + S_RR, 1));
+    /* the one host round trip of the iteration: SolverCG compares ||r|| with the tolerance before it preconditions again */
+    CGC(cudaMemcpyAsync(ctx->h_scalars + S_RR, S + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CGC(cudaStreamSynchronize(ctx->stream));
+    res = sqrt(ctx->h_scalars[S_RR]);
     if (history && it < history_cap) history[it] = res;
     if (res <= tol) { converged = 1; break; }
     if (precond) CG(pmg_vcycle_vmult(precond, z, r)); else CG(pmg_vector_copy(z, r));
-    double rz_new = 0.0;
-    CG(pmg_vector_dot(r, z, &rz_new));
-    const double beta = rz_new / rz;
-    CG(pmg_vector_sadd(p, beta, 1.0, z)); /* p = z + beta p */
-    rz = rz_new;
+    CG(pmg_vector_dot_device(r, z, S_RZNEW));
+    CG(pmgk_scalar_div(S + S_BETA, S + S_RZNEW, S + S_RZ, ctx->stream)); /* beta = r.z (new) / r.z (old) */
+    if (l->active) CG(pmgk_cg_update_p(p->d, z->d, S + S_BETA, l->n_local, ctx->stream)); /* p = z + beta p */
+    CGC(cudaMemcpyAsync(S + S_RZ, S + S_RZNEW, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   }
+#undef CGC
 #undef CG
 done:
   if (last_step) *last_step = it;
