@@ -69,6 +69,9 @@ PMG_HD void pmg_plane_cp_async8(double *smem, unsigned base32, unsigned byte_off
   *(double *)((char *)smem + byte_off) = *src_global;
 #endif
 }
+// (c, d) of one dof, stored and loaded as one 16-byte shared-memory access
+struct alignas(16) PmgPlanePair { double c, d; };
+
 // keeps a per-thread index in its register: without it the compiler, short of registers, recomputes such values from the
 // thread index at every use (ncu: 15 instructions per asynchronous copy)
 #if defined(__CUDA_ARCH__)
@@ -93,7 +96,10 @@ PMG_HD void pmg_plane_stg(double *ptr, double v)
 // held; the first version prefetched one plane through registers and ncu showed 42 % of the stall samples waiting for it)
 // EPF: the epilogue's b / x_old / u of the plane two planes up are prefetched (1: into L2, 2: into L1) while a plane's epilogue
 // runs -- a step or two before they are read; 0: not (the fused step then waits for HBM in every epilogue)
-template <int P, int BX, int BY, int NT_, int FM = -1, int UZ = 1, int LW_ = 0, int NU_ = 3, int EPF = 0>
+// PR: 1 = c and d of a dof are stored side by side and move as one 16-byte shared-memory access (half the LDS / STS
+// instructions of the two sweeps: +11 % at Q3, +2..4 % at Q1 / Q2; at Q4 the aligned register quadruples of the wide loads cost
+// more than they save under the 128-register cap: 118 against 131 GDoF/s, so PR = 0 there: two separate planes)
+template <int P, int BX, int BY, int NT_, int FM = -1, int UZ = 1, int LW_ = 0, int NU_ = 3, int EPF = 0, int PR = 1>
 struct PmgPlaneTile {
   static constexpr int N1 = P + 1;
   static constexpr int NT = NT_;
@@ -118,7 +124,8 @@ struct PmgPlaneTile {
   static constexpr int T = P + 2;                            // position types per direction (inverse-diagonal table)
   static constexpr int NU = NU_, ND = NU_ - 1;               // ring depth, fetch distance
   static_assert(NU_ >= 2 && NU_ <= 8, "ring depth");
-  static constexpr int U_OFFSET = 0, C_OFFSET = NU * UPLANE, O_OFFSET = C_OFFSET + 4 * CPLANE, T_OFFSET = O_OFFSET + NOB * OPLANE;
+  // c and d of a dof sit side by side (one 16-byte access): the c, d buffers start at an even offset
+  static constexpr int U_OFFSET = 0, C_OFFSET = (NU * UPLANE + 1) & ~1, O_OFFSET = C_OFFSET + 4 * CPLANE, T_OFFSET = O_OFFSET + NOB * OPLANE;
   static constexpr int SMEM_DOUBLES = T_OFFSET + T * T * T;
   static constexpr int pick_lw() { int w = XW; while (NT_ % w) ++w; return w; }
   static constexpr int LW = LW_ ? LW_ : pick_lw();           // loader: lanes per u row
@@ -329,23 +336,37 @@ struct PmgPlaneTile {
 #pragma unroll
         for (int i = 0; i < P; ++i) { c[i] = fma(PMG_M(i, j), v, c[i]); d[i] = fma(PMG_KY(i, j), v, d[i]); }
       }
-      double *Co = Cb + st.yo[r];
+      if (PR) {
+        PmgPlanePair *Co = reinterpret_cast<PmgPlanePair *>(Cb) + st.yo[r];
 #pragma unroll
-      for (int i = 0; i < P; ++i) { Co[i] = c[i]; Co[CPLANE + i] = d[i]; }
+        for (int i = 0; i < P; ++i) { PmgPlanePair v; v.c = c[i]; v.d = d[i]; Co[i] = v; }
+      } else {
+        double *Co = Cb + st.yo[r];
+#pragma unroll
+        for (int i = 0; i < P; ++i) { Co[i] = c[i]; Co[CPLANE + i] = d[i]; }
+      }
     }
   }
 
   // ---- x sweep of item (oy, cell xc): c, d columns xc P .. xc P + 2P of row oy -> g, m of the cell row's P nodes ---------
+  // (c, d) of column j of the item's row: one 16-byte load (PR) or two loads from the c and the d plane
+  static PMG_HD PmgPlanePair cd_at(const double *Cc, int j)
+  {
+    if (PR) return reinterpret_cast<const PmgPlanePair *>(Cc)[j * CP];
+    PmgPlanePair v; v.c = Cc[j * CP]; v.d = Cc[CPLANE + j * CP];
+    return v;
+  }
   static PMG_HD void xsweep_item(const PmgSweepParams<P> &p, const double *Cc, double cnt, double *g, double *m)
   {
-    double c = Cc[0], d = Cc[CPLANE];
+    PmgPlanePair v = cd_at(Cc, 0);
+    double c = v.c, d = v.d;
     g[0] = fma(PMG_KX(P, 0), c, PMG_M(P, 0) * d); m[0] = PMG_M(P, 0) * c;
 #pragma unroll
     for (int j = 1; j < P; ++j) {
-      c = Cc[j * CP]; d = Cc[CPLANE + j * CP];
+      v = cd_at(Cc, j); c = v.c; d = v.d;
       g[0] = fma(PMG_KX(P, j), c, fma(PMG_M(P, j), d, g[0])); m[0] = fma(PMG_M(P, j), c, m[0]);
     }
-    c = Cc[P * CP]; d = Cc[CPLANE + P * CP];
+    v = cd_at(Cc, P); c = v.c; d = v.d;
     {
       const double cc = c * cnt, dd = d * cnt;
       g[0] = fma(PMG_KX(0, 0), cc, fma(PMG_M(0, 0), dd, g[0])); m[0] = fma(PMG_M(0, 0), cc, m[0]);
@@ -354,7 +375,7 @@ struct PmgPlaneTile {
     }
 #pragma unroll
     for (int j = 1; j < N1; ++j) {
-      c = Cc[(P + j) * CP]; d = Cc[CPLANE + (P + j) * CP];
+      v = cd_at(Cc, P + j); c = v.c; d = v.d;
 #pragma unroll
       for (int i = 0; i < P; ++i) {
         g[i] = fma(PMG_KX(i, j), c, fma(PMG_M(i, j), d, g[i])); m[i] = fma(PMG_M(i, j), c, m[i]);
@@ -373,7 +394,7 @@ struct PmgPlaneTile {
     for (int r = 0; r < IX; ++r) {
       if (st.xi[r] < 0) continue;
       double g[P], m[P];
-      if (!zero) xsweep_item(p, Cb + st.xi[r], st.xcnt[r], g, m);
+      if (!zero) xsweep_item(p, Cb + (PR ? 2 : 1) * st.xi[r], st.xcnt[r], g, m);
       else {
 #pragma unroll
         for (int i = 0; i < P; ++i) { g[i] = 0.0; m[i] = 0.0; }

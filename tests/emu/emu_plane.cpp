@@ -21,13 +21,13 @@ struct PlaneHostExec {
 
 static bool g_plane_reverse = false;
 
-template <int P, int BX, int BY, int NT, int UZ = 1>
+template <int P, int BX, int BY, int NT, int UZ = 1, int PR = 1>
 static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
                      int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, -1, UZ>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, -1, UZ, 0, 3, 0, PR>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -69,13 +69,13 @@ extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, un
   g_plane_reverse = (small_tiles == 2);
   if (small_tiles == 3) {
     switch (degree) {
-      case 1: plane_go<1, 3, 2, 32, 0>(ARGS); return 0;
-      case 2: plane_go<2, 2, 3, 32, 0>(ARGS); return 0;
+      case 1: plane_go<1, 3, 2, 32, 0, 0>(ARGS); return 0;
+      case 2: plane_go<2, 2, 3, 32, 0, 0>(ARGS); return 0;
       case 3: plane_go<3, 2, 2, 32, 0>(ARGS); return 0;
-      case 4: plane_go<4, 3, 2, 32, 0>(ARGS); return 0;
+      case 4: plane_go<4, 3, 2, 32, 0, 0>(ARGS); return 0;
       case 5: plane_go<5, 2, 2, 32, 0>(ARGS); return 0;
       case 6: plane_go<6, 2, 1, 32, 0>(ARGS); return 0;
-      case 7: plane_go<7, 1, 2, 32, 0>(ARGS); return 0;
+      case 7: plane_go<7, 1, 2, 32, 0, 0>(ARGS); return 0;
       case 8: plane_go<8, 2, 2, 64, 0>(ARGS); return 0;
     }
     return -3;
@@ -97,16 +97,16 @@ extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, un
   // the shipped tiles: the plain apply's for mode 0, the fused modes' otherwise
   if (mode == 0) {
     switch (degree) {
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ) case P: plane_go<P, BX, BY, NT, UZ>(ARGS); return 0;
-#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ)
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR) case P: plane_go<P, BX, BY, NT, UZ, PR>(ARGS); return 0;
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR)
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE
 #undef PMG_PLANE_CASE_F
     }
   } else {
     switch (degree) {
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ)
-#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ) case P: plane_go<P, BX, BY, NT, UZ>(ARGS); return 0;
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR) case P: plane_go<P, BX, BY, NT, UZ, PR>(ARGS); return 0;
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE
 #undef PMG_PLANE_CASE_F
