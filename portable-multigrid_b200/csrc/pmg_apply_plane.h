@@ -99,7 +99,10 @@ PMG_HD void pmg_plane_stg(double *ptr, double v)
 // PR: 1 = c and d of a dof are stored side by side and move as one 16-byte shared-memory access (half the LDS / STS
 // instructions of the two sweeps: +11 % at Q3, +2..4 % at Q1 / Q2; at Q4 the aligned register quadruples of the wide loads cost
 // more than they save under the 128-register cap: 118 against 131 GDoF/s, so PR = 0 there: two separate planes)
-template <int P, int BX, int BY, int NT_, int FM = -1, int UZ = 1, int LW_ = 0, int NU_ = 3, int EPF = 0, int PR = 1>
+// XS: the P nodes of a cell row are shared by XS (1 or 2) x items -- nodes [0, H) and [H, P), H = ceil(P / 2) -- so that the
+// z-sweep accumulators of a thread, H (P+1) doubles, still fit the register file at degrees 7..9 (at the price of the second
+// item re-reading the cell's c, d columns)
+template <int P, int BX, int BY, int NT_, int FM = -1, int UZ = 1, int LW_ = 0, int NU_ = 3, int EPF = 0, int PR = 1, int XS = 1>
 struct PmgPlaneTile {
   static constexpr int N1 = P + 1;
   static constexpr int NT = NT_;
@@ -133,7 +136,9 @@ struct PmgPlaneTile {
   static constexpr int NLD = (YW + LR - 1) / LR;             // passes = u elements a thread loads per plane
   static_assert(NT % LW == 0 && LW >= XW, "loader: LW lanes per row, whole rows per pass");
   static constexpr int NYI = XW * BY, IY = (NYI + NT - 1) / NT; // y items (xl fastest), per thread
-  static constexpr int NXI = OY * BX, IX = (NXI + NT - 1) / NT; // x items (oy fastest), per thread
+  static_assert(XS == 1 || (XS == 2 && P >= 2), "one or two x items per cell row");
+  static constexpr int HN = (P + XS - 1) / XS;               // nodes of a cell row per x item (the first item's; the second takes the rest)
+  static constexpr int NXI = OY * BX * XS, IX = (NXI + NT - 1) / NT; // x items (oy fastest, then cell, then half), per thread
   // epilogue: thread = column tid % OX of rows tid / OX + k ER
   static constexpr int ER = NT / OX;
   static constexpr int NE = (ERW + (ER > 0 ? ER : 1) - 1) / (ER > 0 ? ER : 1);
@@ -151,7 +156,7 @@ struct PmgPlaneTile {
 #define PMG_KZ(i, j) (UZ ? p.Kz[pmg_sweep_canon<P>(i, j)] : p.Kz[(i) * N1 + (j)])
 
   struct ThreadState {
-    double acc[IX][P][N1]; // z sweep: sums of the current layer's planes r = 0..P for node i of the item's cell row
+    double acc[IX][HN][N1]; // z sweep: sums of the current layer's planes r = 0..P for the item's nodes of its cell row
     const double *ld_src;  // loader: the thread's first element (row tid / LW, column tid % LW) of the next plane to fetch
     int ld_off;            // its element offset inside a dof plane
     int ld_dst;            // its byte offset in shared memory (ring slot 0)
@@ -159,7 +164,7 @@ struct PmgPlaneTile {
     int yi[IY];            // y item: offset of its first u row in a u plane | -1
     int yo[IY];            // its first output in a c plane
     double ycnt[IY];       // cells that hold the item's vertex (1 at the mesh boundary, else 2)
-    int xi[IX];            // x item: offset of its first input in a c plane | -1
+    int xi[IX];            // x item: offset of its first input in a c plane | -1; XS = 2: bit 30 set for the second half's item
     int xo[IX];            // its first output in a plane of the output box
     double xcnt[IX];
     int e_off;             // epilogue: element offset of (row tid / OX, column tid % OX) from the tile's first owned dof of a plane
@@ -241,15 +246,16 @@ struct PmgPlaneTile {
       const int item = tid + r * NT;
       st.xi[r] = -1; st.xo[r] = 0; st.xcnt[r] = 1.0;
 #pragma unroll
-      for (int i = 0; i < P; ++i)
+      for (int i = 0; i < HN; ++i)
 #pragma unroll
         for (int q = 0; q < N1; ++q) st.acc[r][i][q] = 0.0;
       if (item < NXI) {
-        const int xc = item / OY, oy = item - xc * OY;
+        const int half = item / (OY * BX), rem = item - half * (OY * BX);
+        const int xc = rem / OY, oy = rem - xc * OY;
         const int gcx = t.cx0 + xc, gy = t.cy0 * P + oy;
         const bool row_ok = gy < p.Ny - 1 || (gy == p.Ny - 1 && t.virt_y);
         if (row_ok && (gcx < p.nx || (gcx == p.nx && t.virt_x))) {
-          st.xi[r] = xc * P * CP + oy;
+          st.xi[r] = (xc * P * CP + oy) | (half << 30);
           st.xo[r] = oy * OP + xc * P;
           st.xcnt[r] = (gcx > 0 && gcx < p.nx) ? 2.0 : 1.0;
         }
@@ -356,29 +362,36 @@ struct PmgPlaneTile {
     PmgPlanePair v; v.c = Cc[j * CP]; v.d = Cc[CPLANE + j * CP];
     return v;
   }
+  // nodes [I0, I1) of the cell row: g[i - I0], m[i - I0].  I0 == 0 includes the cell's low vertex, which also takes the cell below
+  template <int I0, int I1>
   static PMG_HD void xsweep_item(const PmgSweepParams<P> &p, const double *Cc, double cnt, double *g, double *m)
   {
-    PmgPlanePair v = cd_at(Cc, 0);
-    double c = v.c, d = v.d;
-    g[0] = fma(PMG_KX(P, 0), c, PMG_M(P, 0) * d); m[0] = PMG_M(P, 0) * c;
+    PmgPlanePair v;
+    double c, d;
+    if (I0 == 0) {
+      v = cd_at(Cc, 0); c = v.c; d = v.d;
+      g[0] = fma(PMG_KX(P, 0), c, PMG_M(P, 0) * d); m[0] = PMG_M(P, 0) * c;
 #pragma unroll
-    for (int j = 1; j < P; ++j) {
-      v = cd_at(Cc, j); c = v.c; d = v.d;
-      g[0] = fma(PMG_KX(P, j), c, fma(PMG_M(P, j), d, g[0])); m[0] = fma(PMG_M(P, j), c, m[0]);
+      for (int j = 1; j < P; ++j) {
+        v = cd_at(Cc, j); c = v.c; d = v.d;
+        g[0] = fma(PMG_KX(P, j), c, fma(PMG_M(P, j), d, g[0])); m[0] = fma(PMG_M(P, j), c, m[0]);
+      }
     }
     v = cd_at(Cc, P); c = v.c; d = v.d;
     {
-      const double cc = c * cnt, dd = d * cnt;
-      g[0] = fma(PMG_KX(0, 0), cc, fma(PMG_M(0, 0), dd, g[0])); m[0] = fma(PMG_M(0, 0), cc, m[0]);
+      if (I0 == 0) {
+        const double cc = c * cnt, dd = d * cnt;
+        g[0] = fma(PMG_KX(0, 0), cc, fma(PMG_M(0, 0), dd, g[0])); m[0] = fma(PMG_M(0, 0), cc, m[0]);
+      }
 #pragma unroll
-      for (int i = 1; i < P; ++i) { g[i] = fma(PMG_KX(i, 0), c, PMG_M(i, 0) * d); m[i] = PMG_M(i, 0) * c; }
+      for (int i = (I0 == 0 ? 1 : I0); i < I1; ++i) { g[i - I0] = fma(PMG_KX(i, 0), c, PMG_M(i, 0) * d); m[i - I0] = PMG_M(i, 0) * c; }
     }
 #pragma unroll
     for (int j = 1; j < N1; ++j) {
       v = cd_at(Cc, P + j); c = v.c; d = v.d;
 #pragma unroll
-      for (int i = 0; i < P; ++i) {
-        g[i] = fma(PMG_KX(i, j), c, fma(PMG_M(i, j), d, g[i])); m[i] = fma(PMG_M(i, j), c, m[i]);
+      for (int i = I0; i < I1; ++i) {
+        g[i - I0] = fma(PMG_KX(i, j), c, fma(PMG_M(i, j), d, g[i - I0])); m[i - I0] = fma(PMG_M(i, j), c, m[i - I0]);
       }
     }
   }
@@ -387,52 +400,61 @@ struct PmgPlaneTile {
   // zero: the plane is a Dirichlet face (u reads as 0: g = m = 0).  Vertex planes (jz == 0) close the layer below
   // (has_prev; emit: its P planes go to the output box, top: so does the closed sum of the vertex plane itself, the mesh's
   // top plane) and open the layer above (has_next).
+  template <int I0, int I1>
+  static PMG_HD void xz_item(const PmgSweepParams<P> &p, ThreadState &st, int r, const double *Cb, double *Ob, int jz, bool zero,
+                             bool has_prev, bool has_next, bool emit, bool top, int oslot)
+  {
+    constexpr int NI = I1 - I0;
+    double g[NI], m[NI];
+    if (!zero) xsweep_item<I0, I1>(p, Cb + (PR ? 2 : 1) * (st.xi[r] & 0x3FFFFFFF), st.xcnt[r], g, m);
+    else {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) { g[i] = 0.0; m[i] = 0.0; }
+    }
+    if (jz != 0) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int q = 0; q < N1; ++q) st.acc[r][i][q] = fma(PMG_MZ(q, jz), g[i], fma(PMG_KZ(q, jz), m[i], st.acc[r][i][q]));
+    } else {
+      double *Oo = Ob + st.xo[r] + I0;
+      double carry[NI];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) carry[i] = 0.0;
+      if (has_prev) {
+        if (emit) {
+#pragma unroll
+          for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+              Oo[(q == P - 1 ? P - 1 + oslot : q) * OPLANE + i] = fma(PMG_MZ(q, P), g[i], fma(PMG_KZ(q, P), m[i], st.acc[r][i][q]));
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) carry[i] = fma(PMG_MZ(P, P), g[i], fma(PMG_KZ(P, P), m[i], st.acc[r][i][P]));
+        if (top) {
+#pragma unroll
+          for (int i = 0; i < NI; ++i) Oo[(NOB - 1) * OPLANE + i] = carry[i];
+        }
+      }
+      if (has_next) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+#pragma unroll
+          for (int q = 0; q < N1; ++q) st.acc[r][i][q] = fma(PMG_MZ(q, 0), g[i], PMG_KZ(q, 0) * m[i]);
+          st.acc[r][i][0] += carry[i];
+        }
+      }
+    }
+  }
   static PMG_HD void xzsweep(const PmgSweepParams<P> &p, ThreadState &st, const double *Cb, double *Ob, int jz, bool zero,
                              bool has_prev, bool has_next, bool emit, bool top, int oslot)
   {
 #pragma unroll
     for (int r = 0; r < IX; ++r) {
       if (st.xi[r] < 0) continue;
-      double g[P], m[P];
-      if (!zero) xsweep_item(p, Cb + (PR ? 2 : 1) * st.xi[r], st.xcnt[r], g, m);
-      else {
-#pragma unroll
-        for (int i = 0; i < P; ++i) { g[i] = 0.0; m[i] = 0.0; }
-      }
-      if (jz != 0) {
-#pragma unroll
-        for (int i = 0; i < P; ++i)
-#pragma unroll
-          for (int q = 0; q < N1; ++q) st.acc[r][i][q] = fma(PMG_MZ(q, jz), g[i], fma(PMG_KZ(q, jz), m[i], st.acc[r][i][q]));
-      } else {
-        double *Oo = Ob + st.xo[r];
-        double carry[P];
-#pragma unroll
-        for (int i = 0; i < P; ++i) carry[i] = 0.0;
-        if (has_prev) {
-          if (emit) {
-#pragma unroll
-            for (int i = 0; i < P; ++i)
-#pragma unroll
-              for (int q = 0; q < P; ++q)
-                Oo[(q == P - 1 ? P - 1 + oslot : q) * OPLANE + i] = fma(PMG_MZ(q, P), g[i], fma(PMG_KZ(q, P), m[i], st.acc[r][i][q]));
-          }
-#pragma unroll
-          for (int i = 0; i < P; ++i) carry[i] = fma(PMG_MZ(P, P), g[i], fma(PMG_KZ(P, P), m[i], st.acc[r][i][P]));
-          if (top) {
-#pragma unroll
-            for (int i = 0; i < P; ++i) Oo[(NOB - 1) * OPLANE + i] = carry[i];
-          }
-        }
-        if (has_next) {
-#pragma unroll
-          for (int i = 0; i < P; ++i) {
-#pragma unroll
-            for (int q = 0; q < N1; ++q) st.acc[r][i][q] = fma(PMG_MZ(q, 0), g[i], PMG_KZ(q, 0) * m[i]);
-            st.acc[r][i][0] += carry[i];
-          }
-        }
-      }
+      if (XS == 1) xz_item<0, P>(p, st, r, Cb, Ob, jz, zero, has_prev, has_next, emit, top, oslot);
+      else if (!(st.xi[r] >> 30 & 1)) xz_item<0, HN>(p, st, r, Cb, Ob, jz, zero, has_prev, has_next, emit, top, oslot);
+      else xz_item<(XS == 2 ? HN : 0), P>(p, st, r, Cb, Ob, jz, zero, has_prev, has_next, emit, top, oslot);
     }
   }
 

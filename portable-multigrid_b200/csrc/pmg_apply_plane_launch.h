@@ -14,11 +14,11 @@ struct PmgPlaneDeviceExec {
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR>
+template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS>
 __global__ void __launch_bounds__(NT, MINB)
 pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR, XS>;
   extern __shared__ __align__(128) double pmg_plane_smem[];
   PmgPlaneDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -54,12 +54,12 @@ inline void choose_plane_chunks(int tiles, int layers, int slots, int degree, in
   *n_chunks = (layers + lpc - 1) / lpc;
 }
 
-template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR>
+template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS>
 int launch_plane(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                  cudaStream_t stream, int *geom, int part)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR>;
-  auto kernel = pmg_plane_kernel<P, BX, BY, NT, MINB, UZ, FM, PR>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR, XS>;
+  auto kernel = pmg_plane_kernel<P, BX, BY, NT, MINB, UZ, FM, PR, XS>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
   p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
@@ -115,14 +115,14 @@ int PMG_PLANE_CAT(pmg_plane_dispatch_m, PMG_PLANE_TU_MODE)(const pmgk_level *lv,
                                                            double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
   switch (lv->degree) {
-#define PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR) \
-  case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE, PR>(lv, u, b, xold, out, f1, f2, s, geom, part);
+#define PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR, XS) \
+  case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE, PR, XS>(lv, u, b, xold, out, f1, f2, s, geom, part);
 #if PMG_PLANE_TU_MODE == 0
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR)
-#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR)
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR, XS) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR, XS)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR, XS)
 #else
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR)
-#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR)
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR, XS)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR, XS) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR, XS)
 #endif
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE

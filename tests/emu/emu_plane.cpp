@@ -21,13 +21,13 @@ struct PlaneHostExec {
 
 static bool g_plane_reverse = false;
 
-template <int P, int BX, int BY, int NT, int UZ = 1, int PR = 1>
+template <int P, int BX, int BY, int NT, int UZ = 1, int PR = 1, int XS = 1>
 static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
                      int z_own_hi, int n_chunks, const double *M, const double *K, const double *h, int mode,
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, -1, UZ, 0, 3, 0, PR>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, -1, UZ, 0, 3, 0, PR, XS>;
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -59,7 +59,8 @@ static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
 #define ARGS nx, ny, nz, faces, z0, nzl, cz_lo, cz_hi, z_own_lo, z_own_hi, n_chunks, M, K, h, mode, u, b, xold, out, f1, f2, dinv_vec, dinv_tab
 
 // small_tiles: 0 = the tiles csrc/pmg_apply_plane_tiles.inc launches; 1 = tiny tiles and thread counts (several tiles,
-// several items per thread); 2 = tiny tiles, threads run in descending order; 3 = tiny tiles, the layer's steps rolled (UZ = 0)
+// several items per thread); 2 = tiny tiles, threads run in descending order; 3 = tiny tiles, the layer's steps rolled (UZ = 0);
+// 4 = tiny tiles, two x items per cell row (XS = 2)
 extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, unsigned faces, int z0, int nzl,
                          int cz_lo, int cz_hi, int z_own_lo, int z_own_hi, int n_chunks, const double *M,
                          const double *K, const double *h, int mode, const double *u, const double *b,
@@ -67,6 +68,19 @@ extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, un
                          const double *dinv_tab)
 {
   g_plane_reverse = (small_tiles == 2);
+  if (small_tiles == 4) { // two x items per cell row (XS = 2), rolled and unrolled, with and without 16-byte pairs
+    switch (degree) {
+      case 2: plane_go<2, 2, 3, 32, 1, 1, 2>(ARGS); return 0;
+      case 3: plane_go<3, 2, 2, 32, 0, 0, 2>(ARGS); return 0;
+      case 4: plane_go<4, 3, 2, 64, 1, 0, 2>(ARGS); return 0;
+      case 5: plane_go<5, 2, 2, 32, 0, 1, 2>(ARGS); return 0;
+      case 6: plane_go<6, 2, 1, 32, 0, 0, 2>(ARGS); return 0;
+      case 7: plane_go<7, 1, 2, 32, 0, 0, 2>(ARGS); return 0;
+      case 8: plane_go<8, 2, 2, 64, 0, 0, 2>(ARGS); return 0;
+      case 9: plane_go<9, 1, 2, 64, 0, 0, 2>(ARGS); return 0;
+    }
+    return -3;
+  }
   if (small_tiles == 3) {
     switch (degree) {
       case 1: plane_go<1, 3, 2, 32, 0, 0>(ARGS); return 0;
@@ -97,16 +111,16 @@ extern "C" int emu_plane(int degree, int small_tiles, int nx, int ny, int nz, un
   // the shipped tiles: the plain apply's for mode 0, the fused modes' otherwise
   if (mode == 0) {
     switch (degree) {
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR) case P: plane_go<P, BX, BY, NT, UZ, PR>(ARGS); return 0;
-#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR)
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR, XS) case P: plane_go<P, BX, BY, NT, UZ, PR, XS>(ARGS); return 0;
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR, XS)
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE
 #undef PMG_PLANE_CASE_F
     }
   } else {
     switch (degree) {
-#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR)
-#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR) case P: plane_go<P, BX, BY, NT, UZ, PR>(ARGS); return 0;
+#define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR, XS)
+#define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR, XS) case P: plane_go<P, BX, BY, NT, UZ, PR, XS>(ARGS); return 0;
 #include "pmg_apply_plane_tiles.inc"
 #undef PMG_PLANE_CASE
 #undef PMG_PLANE_CASE_F

@@ -214,10 +214,12 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
 
 
 @pytest.mark.parametrize("p", range(1, 9))
-@pytest.mark.parametrize("small,chunks", [(2, 2), (3, 1), (3, 3)])
+@pytest.mark.parametrize("small,chunks", [(2, 2), (3, 1), (3, 3), (4, 1), (4, 2)])
 def test_emulated_plane_kernel_variants(p, small, chunks, emu, oracle):
     """Plane-per-step kernel (csrc/pmg_apply_plane.h): threads of a phase run in descending order (small = 2: a hazard between
     threads of one phase would show), the steps of a cell layer rolled (small = 3); mixed Dirichlet faces, fused step."""
+    if small == 4 and p == 1:
+        pytest.skip("two x items per cell row need two nodes")
     n = (5, 3, 4) if p < 5 else (3, 2, 3)
     for faces in (0x3F, 0x19):
         mf = oracle.MatrixFree(3, p, n, faces=faces)

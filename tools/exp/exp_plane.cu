@@ -21,6 +21,9 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #ifndef C_PR
 #define C_PR 1
 #endif
+#ifndef C_XS
+#define C_XS 1
+#endif
 #ifndef C_FM
 #define C_FM -1
 #endif
@@ -30,7 +33,7 @@ extern "C" void pmg_fe_pencil(int p, double *M, double *K);
 #define STR2(x) #x
 #define STR(x) STR2(x)
 constexpr int P = C_P;
-template <int FM> using TileT = PmgPlaneTile<C_P, C_BX, C_BY, C_NT, FM, C_UZ, 0, C_NU, C_EPF, C_PR>;
+template <int FM> using TileT = PmgPlaneTile<C_P, C_BX, C_BY, C_NT, FM, C_UZ, 0, C_NU, C_EPF, C_PR, C_XS>;
 template <class Tile> struct Ex {
   typename Tile::ThreadState st;
   template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
