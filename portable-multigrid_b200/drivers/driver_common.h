@@ -22,6 +22,51 @@
 
 #define MAXL 32
 
+#include <unistd.h>
+
+/* One process per GPU.  Launched alone the driver takes --device; launched under torchrun / mpirun-like launchers that export
+   RANK, WORLD_SIZE and LOCAL_RANK (e.g. `python -m torch.distributed.run --no-python --nproc-per-node 8 ... bin/driver ...`)
+   the ranks form one slab-distributed context: rank 0 creates the ncclUniqueId and hands it to the others through a file
+   (PMG_NCCL_ID_FILE, default /tmp/pmg_nccl_id.<MASTER_PORT>; one node: a shared /tmp).  g_rank != 0 prints nothing. */
+static int g_rank = 0, g_world = 1;
+static int driver_make_context(pmg_context **ctx, int device_arg)
+{
+  const char *er = getenv("RANK"), *ew = getenv("WORLD_SIZE"), *el = getenv("LOCAL_RANK");
+  g_rank = er ? atoi(er) : 0;
+  g_world = ew ? atoi(ew) : 1;
+  if (g_world <= 1) return pmg_context_create(ctx, device_arg);
+  char path[512];
+  const char *pf = getenv("PMG_NCCL_ID_FILE"), *port = getenv("MASTER_PORT");
+  if (pf) snprintf(path, sizeof(path), "%s", pf);
+  else snprintf(path, sizeof(path), "/tmp/pmg_nccl_id.%s", port ? port : "0");
+  unsigned char id[128];
+  if (g_rank == 0) {
+    char tmp[600];
+    snprintf(tmp, sizeof(tmp), "%s.tmp.%d", path, (int)getpid());
+    int rc = pmg_nccl_unique_id(id);
+    if (rc != PMG_OK) return rc;
+    FILE *f = fopen(tmp, "wb");
+    if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) { if (f) fclose(f); return PMG_ERR_ARG; }
+    fclose(f);
+    if (rename(tmp, path) != 0) return PMG_ERR_ARG; /* atomic: readers see the whole id or nothing */
+  } else {
+    size_t got = 0;
+    for (int tries = 0; tries < 6000 && got != sizeof(id); ++tries) { /* up to 60 s */
+      FILE *f = fopen(path, "rb");
+      if (f) { got = fread(id, 1, sizeof(id), f); fclose(f); }
+      if (got != sizeof(id)) usleep(10000);
+    }
+    if (got != sizeof(id)) { fprintf(stderr, "rank %d: no ncclUniqueId in %s\n", g_rank, path); return PMG_ERR_ARG; }
+  }
+  const int rc = pmg_context_create_distributed(ctx, el ? atoi(el) : g_rank, g_rank, g_world, id);
+  if (g_rank == 0 && rc == PMG_OK) { /* everyone has joined the communicator: the file has served */
+    unlink(path);
+  }
+  return rc;
+}
+/* printf on rank 0 only */
+#define RPRINT(...) do { if (g_rank == 0) printf(__VA_ARGS__); } while (0)
+
 typedef struct { int degree, n; } level_t;
 
 static double now_s(void)
@@ -103,19 +148,19 @@ static int solve_hierarchy(pmg_context *ctx, const level_t *lv, int L, int pre, 
   CK(pmg_cg_solve(A, x, rhs, mg, (int)(n_dofs > 100000 ? 100000 : n_dofs), g_tol * bnorm, &last_step, NULL, 0));
   CK(pmg_sync(ctx));
   const double dt = now_s() - t0;
-  printf("  Solver converged in %d iterations.\n", last_step);
+  RPRINT("  Solver converged in %d iterations.\n", last_step);
   double norm = 0.0;
   CK(pmg_laplace_operator_solution_norm(A, x, &norm));
-  printf("  solution norm: %.10g\n", norm);
-  printf("  [b200] solve time %.3f ms, %.3f GDoF/s (DoFs x iterations / time)\n", dt * 1e3, (double)n_dofs * last_step / dt / 1e9);
+  RPRINT("  solution norm: %.10g\n", norm);
+  RPRINT("  [b200] solve time %.3f ms on %d GPU(s), %.3f GDoF/s (DoFs x iterations / time)\n", dt * 1e3, g_world, (double)n_dofs * last_step / dt / 1e9);
   if (g_profile) {
     double ms[MAXL * 4];
     pmg_vector *z;
     CK(pmg_laplace_operator_initialize_dof_vector(A, &z));
     CK(pmg_vcycle_profile(mg, z, rhs, ms, MAXL));
-    printf("  [b200] one V-cycle, device ms per level (smoother / transfer / halo / other):\n");
+    RPRINT("  [b200] one V-cycle, device ms on rank 0 per level (smoother / transfer / halo / other):\n");
     for (int l = L - 1; l >= 0; --l)
-      printf("    level %2d  Q%d %4d^d cells: %9.4f %9.4f %9.4f %9.4f\n", l, lv[l].degree, lv[l].n, ms[l * 4], ms[l * 4 + 1], ms[l * 4 + 2], ms[l * 4 + 3]);
+      RPRINT("    level %2d  Q%d %4d^d cells: %9.4f %9.4f %9.4f %9.4f\n", l, lv[l].degree, lv[l].n, ms[l * 4], ms[l * 4 + 1], ms[l * 4 + 2], ms[l * 4 + 3]);
     pmg_vector_destroy(z);
   }
   pmg_vector_destroy(rhs); pmg_vector_destroy(x);

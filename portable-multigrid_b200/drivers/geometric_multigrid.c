@@ -11,17 +11,17 @@
 
 static int run_degree(pmg_context *ctx, int degree, int cycles, int pre, int post, int cheb)
 {
-  printf("============== fe_degree = %d ============== \n\n", degree);
+  RPRINT("============== fe_degree = %d ============== \n\n", degree);
   for (int cycle = 0; cycle < cycles; ++cycle) {
-    printf("\n\nCycle %d\n", cycle);
+    RPRINT("\n\nCycle %d\n", cycle);
     level_t lv[MAXL];
     const int L = cycle + 1; /* create_geometric_coarsening_sequence: 1, 2, 4, ... cells per direction */
     for (int l = 0; l < L; ++l) { lv[l].degree = degree; lv[l].n = 1 << l; }
-    printf(" Number of degrees of freedom: %lld (by level: ", n_dofs_of(degree, lv[L - 1].n));
-    for (int l = 0; l < L; ++l) printf("%lld%s", n_dofs_of(degree, lv[l].n), l == L - 1 ? ")" : ", ");
-    printf("\n");
+    RPRINT(" Number of degrees of freedom: %lld (by level: ", n_dofs_of(degree, lv[L - 1].n));
+    for (int l = 0; l < L; ++l) RPRINT("%lld%s", n_dofs_of(degree, lv[l].n), l == L - 1 ? ")" : ", ");
+    RPRINT("\n");
     if (solve_hierarchy(ctx, lv, L, pre, post, cheb)) return 1;
-    printf("\n");
+    RPRINT("\n");
   }
   return 0;
 }
@@ -36,7 +36,7 @@ int main(int argc, char **argv)
   common_options(argc, argv);
   g_dim = arg_int(argc, argv, "--dim", 3);
   pmg_context *ctx;
-  CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
+  CK(driver_make_context(&ctx, arg_int(argc, argv, "--device", 0)));
   for (int d = (only ? only : 1); d <= (only ? only : max_degree); ++d)
     if (run_degree(ctx, d, cycles, pre, post, cheb)) return 1;
   pmg_context_destroy(ctx);

@@ -21,11 +21,13 @@ int main(int argc, char **argv)
   if (mg_levels > fe_degree) mg_levels = fe_degree; /* Assert(mg_levels <= fe_degree) (:140-142) */
   common_options(argc, argv);
   g_dim = arg_int(argc, argv, "--dim", 2);
+  /* --cells N: one run on an N^dim mesh instead of the reference's cycles over 2^cycle cells (BASELINE config 5: N = 160) */
+  const int cells_arg = arg_int(argc, argv, "--cells", 0);
   pmg_context *ctx;
-  CK(pmg_context_create(&ctx, arg_int(argc, argv, "--device", 0)));
-  for (int cycle = 0; cycle < cycles; ++cycle) {
-    printf("\n\nCycle %d\n", cycle);
-    const int n = 1 << cycle;
+  CK(driver_make_context(&ctx, arg_int(argc, argv, "--device", 0)));
+  for (int cycle = 0; cycle < (cells_arg > 0 ? 1 : cycles); ++cycle) {
+    RPRINT("\n\nCycle %d\n", cycle);
+    const int n = cells_arg > 0 ? cells_arg : 1 << cycle;
     level_t lv[MAXL];
     int L = 0;
     if (hp) {
@@ -39,9 +41,9 @@ int main(int argc, char **argv)
       for (int l = 0; l < mg_levels; ++l) { lv[L].degree = fe_degree - (mg_levels - 1 - l); lv[L].n = n; ++L; }
     }
     for (int l = 0; l < L; ++l)
-      printf("level %d: p = %d, DoFs = %lld\n", l, lv[l].degree, n_dofs_of(lv[l].degree, lv[l].n));
+      RPRINT("level %d: p = %d, DoFs = %lld\n", l, lv[l].degree, n_dofs_of(lv[l].degree, lv[l].n));
     if (solve_hierarchy(ctx, lv, L, pre, post, cheb)) return 1;
-    printf("\n");
+    RPRINT("\n");
   }
   pmg_context_destroy(ctx);
   return 0;

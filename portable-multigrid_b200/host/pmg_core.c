@@ -413,6 +413,12 @@ int pmg_vector_mean_value(const pmg_vector *x, double *result)
 /* ---- halo exchange ------------------------------------------------------------ */
 int pmg_halo_update(pmg_context *ctx, const pmg_layout *lay, double *d)
 {
+  if (ctx->halo_hook && ctx->has_comm && !lay->gathered && lay->active) {
+    ctx->halo_hook(ctx->halo_hook_user, 1);
+    const int rc = pmg_halo_update_on(ctx, lay, d, ctx->comm, ctx->stream);
+    ctx->halo_hook(ctx->halo_hook_user, 0);
+    return rc;
+  }
   return pmg_halo_update_on(ctx, lay, d, ctx->comm, ctx->stream);
 }
 

@@ -94,6 +94,9 @@ struct pmg_context {
   ncclComm_t halo_comm;
   cudaEvent_t ev_ready, ev_halo;
   int overlap;
+  /* profiling hook (pmg_vcycle_profile): called with 1 before and 0 after every ghost exchange enqueued on ctx->stream */
+  void (*halo_hook)(void *user, int begin);
+  void *halo_hook_user;
   int64_t coarse_threshold;
   double *work;      /* device: reduction workspace */
   double *scalars;   /* device: small scalar slots */

@@ -39,6 +39,7 @@ struct pmg_vcycle {
   double *pinned_in, *pinned_out;
   /* profiling */
   int profiling;
+  int cur_level, cur_cat; /* the phase the last mark() opened */
   int n_marks;
   cudaEvent_t ev[4096];
   int mark_level[4096], mark_cat[4096];
@@ -64,6 +65,7 @@ static int mark(pmg_vcycle *v, int level, int cat)
 {
   nvtx_phase(v, level, cat);
   if (!v->profiling) return PMG_OK;
+  if (cat != CAT_HALO) { v->cur_level = level; v->cur_cat = cat; }
   if (v->n_marks >= 4096) return PMG_OK;
   const int i = v->n_marks++;
   PMG_CUDA(cudaEventCreate(&v->ev[i]));
@@ -313,13 +315,25 @@ int pmg_vcycle_vmult_host_owned(pmg_vcycle *v, double *dst_host_owned, const dou
   return pmg_vector_export_owned(v->host_dst, dst_host_owned);
 }
 
+/* ghost exchanges inside a phase are booked to the level's halo column: device time between the exchange's enqueue points on
+   the compute stream, so it includes waiting for the neighbour ranks to arrive */
+static void profile_halo_hook(void *user, int begin)
+{
+  pmg_vcycle *v = (pmg_vcycle *)user;
+  if (!v->profiling || v->cur_cat < 0) return;
+  if (begin) (void)mark(v, v->cur_level, CAT_HALO);
+  else (void)mark(v, v->cur_level, v->cur_cat);
+}
+
 int pmg_vcycle_profile(pmg_vcycle *v, pmg_vector *dst, const pmg_vector *src, double *out_ms, int cap_levels)
 {
   if (!v || !out_ms || cap_levels < v->n_levels) return PMG_ERR_ARG;
   PMG_CHECK(ensure_initialized(v));
   memset(out_ms, 0, sizeof(double) * 4 * cap_levels);
-  v->profiling = 1; v->n_marks = 0;
+  v->profiling = 1; v->n_marks = 0; v->cur_cat = -1;
+  v->ctx->halo_hook = profile_halo_hook; v->ctx->halo_hook_user = v;
   int rc = pmg_vcycle_vmult(v, dst, src);
+  v->ctx->halo_hook = NULL; v->ctx->halo_hook_user = NULL;
   if (!rc) rc = mark(v, 0, -1);
   v->profiling = 0;
   if (rc) return rc;
