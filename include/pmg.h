@@ -76,6 +76,8 @@ int pmg_context_set_coarse_threshold(pmg_context *ctx, int64_t n_dofs);
 void *pmg_context_stream(pmg_context *ctx); /* cudaStream_t */
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t pmg_context_launch_count(const pmg_context *ctx);
+/* applies launched so far that exchanged ghost planes by the fused push (no exchange of their own), see pmg_chebyshev_vmult */
+int64_t pmg_context_fused_halo_count(const pmg_context *ctx);
 
 /* ---- LaplaceOperator (include/operators/portable_laplace_operator.h:383-461) ---- */
 /* ctor (DoFHandler, AffineConstraints, overlap) :463-485.  coefficient: 0 = constant (reference),

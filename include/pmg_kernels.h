@@ -56,6 +56,23 @@ enum { PMGK_PART_ALL = 0, PMGK_PART_INTERIOR = 1, PMGK_PART_BOUNDARY = 2 };
 int pmgk_apply_part(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                     double *out, double f1, double f2, int part, void *stream);
 int pmgk_apply_splits(const pmgk_level *lv, int mode);
+/* Fused compute + ghost exchange (plane-per-step kernel, slabs with neighbours): the launch stores its boundary planes of
+   `out` straight into the neighbours' ghost planes over NVLink (push != 0) and, with consume != 0, takes u's ghost planes as
+   already pushed by the neighbours' previous fused launch (its boundary chunks wait for their flag; no exchange of u before
+   the launch).  out_lower / out_upper: the neighbours' copies of `out` as mapped here (NULL: no neighbour), lower_z0 /
+   upper_z0: their first stored planes; mailbox*: 16 flag words per rank, zero-initialised (words 8..11 are used here).
+   Every rank must issue the same sequence of fused launches.  Replaces update_ghost_values() + vmult of the reference
+   (include/operators/portable_laplace_operator.h:635-661) inside the smoother.
+   pmgk_apply_can_push: 1 if the level's launch supports it. */
+typedef struct pmgk_push {
+  double *out_lower, *out_upper;
+  int lower_z0, upper_z0;
+  void *mailbox, *mailbox_lower, *mailbox_upper;
+  int push, consume;
+} pmgk_push;
+int pmgk_apply_push(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                    double *out, double f1, double f2, const pmgk_push *push, void *stream);
+int pmgk_apply_can_push(const pmgk_level *lv, int mode);
 /* number of kernel launches pmgk_apply issues (1) and the launch geometry it would use */
 int pmgk_apply_geometry(const pmgk_level *lv, int *grid, int *block, int *smem_bytes, int *n_chunks);
 

@@ -196,6 +196,33 @@ extern "C" int pmgk_apply_part(const pmgk_level *lv, int mode, const double *u, 
   return dispatch(lv, mode, u, b, xold, out, f1, f2, (cudaStream_t)stream, nullptr, part);
 }
 
+thread_local const pmgk_push *pmg_tl_push = nullptr;
+
+static bool plane_kernel_level(const pmgk_level *lv)
+{
+  const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
+  const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
+  return lv->dim == 3 && !lv->coef && lv->degree <= PMG_PLANE_MAX_DEGREE && (lv->tile_variant == 6 || (lv->tile_variant == 0 && !small_level));
+}
+
+extern "C" int pmgk_apply_can_push(const pmgk_level *lv, int mode)
+{
+  return lv && (mode == PMGK_RESIDUAL || mode == PMGK_CHEB_FIRST || mode == PMGK_CHEB_STEP) && plane_kernel_level(lv) && lv->cz_hi - lv->cz_lo >= 2;
+}
+
+extern "C" int pmgk_apply_push(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
+                               double *out, double f1, double f2, const pmgk_push *push, void *stream)
+{
+  if (!lv || !u || !out || !push) return PMG_ERR_ARG;
+  if (mode != PMGK_APPLY && !b) return PMG_ERR_ARG;
+  if (u == out) return PMG_ERR_ARG;
+  if (!pmgk_apply_can_push(lv, mode)) return PMG_ERR_UNSUPPORTED;
+  pmg_tl_push = push;
+  const int rc = dispatch(lv, mode, u, b, xold, out, f1, f2, (cudaStream_t)stream, nullptr);
+  pmg_tl_push = nullptr;
+  return rc;
+}
+
 extern "C" int pmgk_apply_splits(const pmgk_level *lv, int mode)
 {
   int g[4] = {0, 0, 0, 0};

@@ -102,7 +102,9 @@ PMG_HD void pmg_plane_stg(double *ptr, double v)
 // XS: the P nodes of a cell row are shared by XS (1 or 2) x items -- nodes [0, H) and [H, P), H = ceil(P / 2) -- so that the
 // z-sweep accumulators of a thread, H (P+1) doubles, still fit the register file at degrees 7..9 (at the price of the second
 // item re-reading the cell's c, d columns)
-template <int P, int BX, int BY, int NT_, int FM = -1, int UZ = 1, int LW_ = 0, int NU_ = 3, int EPF = 0, int PR = 1, int XS = 1>
+// PUSH: 1 = the epilogue also stores the slab's boundary planes into the neighbours' ghost planes (p.push_lo / p.push_hi: fused
+// ghost exchange, csrc/pmg_apply_plane_launch.h); a separate instance, so that launches without it carry none of its code
+template <int P, int BX, int BY, int NT_, int FM = -1, int UZ = 1, int LW_ = 0, int NU_ = 3, int EPF = 0, int PR = 1, int XS = 1, int PUSH = 0>
 struct PmgPlaneTile {
   static constexpr int N1 = P + 1;
   static constexpr int NT = NT_;
@@ -528,6 +530,14 @@ struct PmgPlaneTile {
     // plane bases (uniform) + 32-bit element indices (a local vector holds < 2^31 dofs)
     const double *pu = p.u + eoff + st.e_off, *pd = (MODE >= PMG_MODE_CHEB_FIRST && p.dinv_vec) ? p.dinv_vec + eoff + st.e_off : nullptr;
     double *po = p.out + eoff + st.e_off;
+    // the neighbour's copy of this plane, when it holds it as a ghost plane (fused ghost push; a slab has >= 2 cell layers,
+    // so a plane goes to at most one neighbour)
+    double *pqb = nullptr;
+    if (PUSH) {
+      if (p.push_lo && gz == p.z_own_lo) pqb = p.push_lo;
+      else if (p.push_hi && gz >= p.z_own_hi - P) pqb = p.push_hi;
+    }
+    double *pq = (PUSH && pqb) ? pqb + eoff + st.e_off : nullptr;
     PMG_OPAQUE_PTR(pu); PMG_OPAQUE_PTR(pd); PMG_OPAQUE_PTR(po);
     const int rstep = ER * p.Nx;
 #pragma unroll
@@ -542,7 +552,9 @@ struct PmgPlaneTile {
         if (NA >= 3 && has_xo) xo = st.ein[2][k];
         if (MODE >= PMG_MODE_CHEB_FIRST) dinv = pd ? pmg_plane_ldg(pd + g) : Tz[T * (st.e_ty >> (4 * k) & 0xFu)];
         const double y = Os[k * ER * OP];
-        pmg_plane_stg(po + g, epi_value<MODE>(p, y, uc, bb, xo, dir, dinv));
+        const double val = epi_value<MODE>(p, y, uc, bb, xo, dir, dinv);
+        pmg_plane_stg(po + g, val);
+        if (PUSH && pq) pmg_plane_stg(pq + g, val);
       }
     }
     if (DIR && t.xextra && tid < ERW) { // the mesh's last vertex line in x: Dirichlet dofs (identity rows), read directly
@@ -552,7 +564,9 @@ struct PmgPlaneTile {
         const double uc = pmg_plane_ldg(p.u + g);
         const double bb = (MODE != PMG_MODE_APPLY) ? pmg_plane_ldg(p.b + g) : 0.0;
         const double xo = has_xo ? pmg_plane_ldg(p.xold + g) : 0.0;
-        pmg_plane_stg(p.out + g, epi_value<MODE>(p, 0.0, uc, bb, xo, true, 1.0));
+        const double val = epi_value<MODE>(p, 0.0, uc, bb, xo, true, 1.0);
+        pmg_plane_stg(p.out + g, val);
+        if (PUSH && pqb) pmg_plane_stg(pqb + g, val);
       }
     }
   }

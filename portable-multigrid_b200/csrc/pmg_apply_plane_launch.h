@@ -14,11 +14,24 @@ struct PmgPlaneDeviceExec {
   __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
-template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS>
+// flag words of the fused ghost exchange in a rank's mailbox (words 0..5 belong to the stand-alone push kernel, csrc/pmg_halo.cu)
+enum { PMG_FUSED_FROM_LO = 8, PMG_FUSED_FROM_HI = 9, PMG_FUSED_EPOCH = 10, PMG_FUSED_TICKET = 11 };
+__device__ __forceinline__ void pmg_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pmg_ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS, int PUSH>
 __global__ void __launch_bounds__(NT, MINB)
 pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, int chunk_stride)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR, XS>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR, XS, PUSH>;
   extern __shared__ __align__(128) double pmg_plane_smem[];
   PmgPlaneDeviceExec<Tile> ex;
   const int b = blockIdx.x;
@@ -26,8 +39,45 @@ pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, i
   const int tile_y = (b / p.tiles_x) % p.tiles_y;
   // the launch's CTAs work on z-chunks chunk_first + i * chunk_stride (all chunks: 0, 1; the two chunks that read the slab's
   // ghost planes: 0, n_chunks - 1; the others: 1, 1)
-  const int chunk = chunk_first + (b / (p.tiles_x * p.tiles_y)) * chunk_stride;
+  const int group = b / (p.tiles_x * p.tiles_y);
+  int chunk = chunk_first + group * chunk_stride;
+  // ---- fused ghost exchange (p.mb: whole launches of slabs with neighbours) ---------------------------------------------
+  // The chunks that touch the slab's ends go FIRST (groups 0 and 1), the others after them: the boundary planes are on their
+  // way over NVLink while the bulk of the launch computes, and by the time the neighbours' next launch needs them they have
+  // long arrived.  Flag words (PMG_FUSED_*): the neighbours write FROM_LO / FROM_HI of my mailbox = the number of fused
+  // launches whose boundary chunks they have completed; EPOCH = my own count.  All ranks issue the same launches.
+  bool boundary = false;
+  if (PUSH && p.mb) {
+    chunk = group == 0 ? 0 : group == 1 ? p.n_chunks - 1 : group - 1;
+    const bool at_lo = chunk == 0, at_hi = chunk == p.n_chunks - 1;
+    boundary = at_lo || at_hi;
+    if (boundary && p.consume) {
+      // u's ghost planes were pushed by the neighbours' previous fused launch: wait until they say it is complete.  That
+      // also tells me that they have stopped reading the ghost planes my own pushes of this launch overwrite (the vector
+      // written now was last read as u two launches ago).
+      if (threadIdx.x == 0) {
+        const unsigned long long e = pmg_ld_acquire_sys(p.mb + PMG_FUSED_EPOCH);
+        if (at_lo && p.mb_lo) while (pmg_ld_acquire_sys(p.mb + PMG_FUSED_FROM_LO) < e) { }
+        if (at_hi && p.mb_hi) while (pmg_ld_acquire_sys(p.mb + PMG_FUSED_FROM_HI) < e) { }
+      }
+      __syncthreads();
+    }
+  }
   Tile::run(p, ex, pmg_plane_smem, tile_x, tile_y, chunk);
+  if (!PUSH || !boundary) return;
+  __threadfence_system(); // this thread's peer stores are visible system-wide before its CTA takes a ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long n_boundary = (unsigned long long)p.tiles_x * p.tiles_y * (p.n_chunks > 1 ? 2 : 1);
+    if (atomicAdd(p.mb + PMG_FUSED_TICKET, 1ull) == n_boundary - 1) { // the last boundary CTA: everything is fenced
+      p.mb[PMG_FUSED_TICKET] = 0;
+      const unsigned long long e = pmg_ld_acquire_sys(p.mb + PMG_FUSED_EPOCH) + 1;
+      __threadfence_system();
+      if (p.mb_lo) pmg_st_release_sys(p.mb_lo + PMG_FUSED_FROM_HI, e); // I am my lower neighbour's upper neighbour
+      if (p.mb_hi) pmg_st_release_sys(p.mb_hi + PMG_FUSED_FROM_LO, e);
+      pmg_st_release_sys(p.mb + PMG_FUSED_EPOCH, e);
+    }
+  }
 }
 
 // z-chunks of a launch.  Measured on B200 (profiles/r02_plane_chunk_sweep.txt, Q4): one wave of CTAs that each march the
@@ -54,12 +104,12 @@ inline void choose_plane_chunks(int tiles, int layers, int slots, int degree, in
   *n_chunks = (layers + lpc - 1) / lpc;
 }
 
-template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS>
+template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS, int PUSH>
 int launch_plane(const pmgk_level *lv, const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                  cudaStream_t stream, int *geom, int part)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR, XS>;
-  auto kernel = pmg_plane_kernel<P, BX, BY, NT, MINB, UZ, FM, PR, XS>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, FM, UZ, 0, 3, 0, PR, XS, PUSH>;
+  auto kernel = pmg_plane_kernel<P, BX, BY, NT, MINB, UZ, FM, PR, XS, PUSH>;
   PmgSweepParams<P> p;
   p.nx = lv->nx; p.ny = lv->ny; p.nz = lv->nz;
   p.Nx = lv->Nx; p.Ny = lv->Ny; p.Nz = lv->Nz;
@@ -88,6 +138,17 @@ int launch_plane(const pmgk_level *lv, const double *u, const double *b, const d
   pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
   p.mode = (FM == 4) ? PMG_MODE_CHEB_STEP : FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
+  // fused ghost push (pmgk_apply_push): whole launches of slabs with at least two cell layers
+  p.push_lo = p.push_hi = nullptr; p.mb = p.mb_lo = p.mb_hi = nullptr; p.consume = 0;
+  if (const pmgk_push *ps = PUSH ? pmg_tl_push : nullptr) {
+    if (part != PMGK_PART_ALL || lv->cz_hi - lv->cz_lo < 2 || !ps->mailbox) return PMG_ERR_UNSUPPORTED;
+    const int64_t plane = (int64_t)lv->Nx * lv->Ny;
+    if (ps->push && ps->out_lower) p.push_lo = ps->out_lower + plane * (lv->z0 - ps->lower_z0);
+    if (ps->push && ps->out_upper) p.push_hi = ps->out_upper + plane * (lv->z0 - ps->upper_z0);
+    p.mb = (unsigned long long *)ps->mailbox;
+    p.mb_lo = (unsigned long long *)ps->mailbox_lower; p.mb_hi = (unsigned long long *)ps->mailbox_upper;
+    p.consume = ps->consume;
+  }
   // a launch in parts (halo exchange overlapped with the chunks that read no ghost plane, host/pmg_operator.c): the first and
   // the last chunk read the slab's ghost planes, the others run while those are in flight
   int chunk_first = 0, chunk_stride = 1, chunk_count = p.n_chunks;
@@ -115,8 +176,16 @@ int PMG_PLANE_CAT(pmg_plane_dispatch_m, PMG_PLANE_TU_MODE)(const pmgk_level *lv,
                                                            double *out, double f1, double f2, cudaStream_t s, int *geom, int part)
 {
   switch (lv->degree) {
+// the residual and the Chebyshev steps (modes 1 .. 4) come in a second instance with the fused ghost exchange (pmgk_apply_push)
+#if PMG_PLANE_TU_MODE >= 1
+#define PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR, XS)                                                                              \
+  case P:                                                                                                                             \
+    return pmg_tl_push ? launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE, PR, XS, 1>(lv, u, b, xold, out, f1, f2, s, geom, part) \
+                       : launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE, PR, XS, 0>(lv, u, b, xold, out, f1, f2, s, geom, part);
+#else
 #define PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR, XS) \
-  case P: return launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE, PR, XS>(lv, u, b, xold, out, f1, f2, s, geom, part);
+  case P: return pmg_tl_push ? PMG_ERR_UNSUPPORTED : launch_plane<P, BX, BY, NT, MINB, UZ, PMG_PLANE_TU_MODE, PR, XS, 0>(lv, u, b, xold, out, f1, f2, s, geom, part);
+#endif
 #if PMG_PLANE_TU_MODE == 0
 #define PMG_PLANE_CASE(P, BX, BY, NT, MINB, UZ, PR, XS) PMG_PLANE_LAUNCH(P, BX, BY, NT, MINB, UZ, PR, XS)
 #define PMG_PLANE_CASE_F(P, BX, BY, NT, MINB, UZ, PR, XS)

@@ -158,6 +158,15 @@ struct PmgSweepParams {
   double f1, f2;
   const double *dinv_vec; // explicit inverse diagonal, or NULL => table
   const double *dinv_tab; // (P+2)^3 table indexed by 1-D position types
+  // Fused ghost push (plane-per-step kernel; NULL = none): the slab neighbours' copies of `out`, mapped over NVLink.  The
+  // epilogue stores plane z_own_lo also into push_lo (the lower neighbour holds it as its upper ghost plane) and planes
+  // [z_own_hi - P, z_own_hi) into push_hi (the upper neighbour's lower ghost planes), both indexed like `out`: the launcher
+  // folds the difference of the slabs' first stored planes into the pointers.  The neighbours' next apply then finds its
+  // ghost planes filled and needs no exchange (reference: update_ghost_values before every vmult, :661).
+  double *push_lo, *push_hi;
+  // flag words that order the fused pushes (csrc/pmg_apply_plane_launch.h): this rank's mailbox and the neighbours'
+  unsigned long long *mb, *mb_lo, *mb_hi;
+  int consume; // u's ghost planes were pushed by the neighbours' previous fused launch: the boundary chunks wait for its flag
 };
 
 // fill the five 1-D matrices from the reference-cell pencil (Mref, Kref) and the cell sizes h; entries related by the

@@ -96,6 +96,7 @@ int launch_sweep(const pmgk_level *lv, const double *u, const double *b, const d
   pmg_sweep_fill_matrices<P>(p, lv->Mref, lv->Kref, lv->h);
   p.mode = FM; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = lv->dinv_vec; p.dinv_tab = lv->dinv_tab;
+  p.push_lo = p.push_hi = nullptr; p.mb = p.mb_lo = p.mb_hi = nullptr; p.consume = 0; // fused ghost push: plane kernel only
   int chunk_first = 0, chunk_stride = 1, chunk_count = p.n_chunks;
   if (part != PMGK_PART_ALL) {
     if (p.n_chunks < 3) return PMG_ERR_UNSUPPORTED;

@@ -16,3 +16,8 @@ extern "C" void pmg_count_launch(int n);
       return PMG_ERR_CUDA;                                                                   \
     }                                                                                        \
   } while (0)
+
+/* the fused-push descriptor of the pmgk_apply_push call in progress on this thread (csrc/pmg_apply.cu), read by the plane
+   kernel's launcher; NULL for every other launch */
+#include "pmg_kernels.h"
+extern thread_local const pmgk_push *pmg_tl_push;

@@ -164,6 +164,7 @@ int pmg_context_set_coarse_threshold(pmg_context *ctx, int64_t n_dofs)
 
 void *pmg_context_stream(pmg_context *ctx) { return ctx ? (void *)ctx->stream : NULL; }
 /* kernels and collectives this PROCESS has enqueued (all contexts, all threads; the counter is atomic) */
+int64_t pmg_context_fused_halo_count(const pmg_context *ctx) { return ctx ? ctx->p2p.n_fused : 0; }
 int64_t pmg_context_launch_count(const pmg_context *ctx) { (void)ctx; return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 /* ---- partition -------------------------------------------------------------- */

@@ -75,12 +75,15 @@ typedef struct pmg_p2p_reg {
   int in_use;                         /* 0: released by its vector, kept (mapped on the neighbours) for the next vector of that level */
 } pmg_p2p_reg;
 typedef struct pmg_p2p {
-  int enabled;
+  int enabled;                        /* the neighbours' mailboxes (and, per vector, arrays) are mapped */
+  int explicit_push;                  /* stand-alone exchanges use the push kernel instead of the NCCL group (PMG_P2P_HALO=1) */
+  int fused;                          /* the smoother's applies push their boundary planes themselves (PMG_FUSED_HALO, default on) */
   void *msg_dev;                      /* device scratch of the handle exchange */
   uint64_t *mailbox, *mb_lower, *mb_upper;
   pmg_p2p_reg reg[PMG_P2P_MAX_REG];
   int n_reg;
   const double *last_base;            /* the array of the previous exchange (NULL: unknown) */
+  int64_t n_fused;                    /* applies that consumed pushed ghost planes (statistics) */
 } pmg_p2p;
 
 struct pmg_context {
@@ -129,6 +132,8 @@ double *pmg_p2p_acquire(pmg_context *ctx, const pmg_layout *lay);
 int pmg_p2p_release(pmg_context *ctx, double *d);
 int pmg_p2p_halo(pmg_context *ctx, const pmg_layout *lay, double *d, cudaStream_t stream, int *done);
 void pmg_p2p_forget(pmg_context *ctx);
+/* 1 and *desc filled (push / consume left 0) if `out` is a mapped vector of a slab with neighbours and fused pushes are on */
+int pmg_p2p_push_desc(pmg_context *ctx, const pmg_layout *lay, double *out, pmgk_push *desc);
 
 struct pmg_vector {
   pmg_context *ctx;
@@ -177,11 +182,16 @@ int pmg_allreduce_sum(pmg_context *ctx, double *dev_scalar, int count);
 int pmg_vector_dot_device(const pmg_vector *x, const pmg_vector *y, int slot);
 /* ghost update of u + fused apply; the exchange overlaps the interior z-chunks when the launch splits (pmg_operator.c) */
 int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1, double f2);
+int pmg_apply_chain_ok(const pmg_operator *op, int mode, double *v0, double *v1);
+int pmg_apply_chained(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1,
+                      double f2, int consume, int push);
 int pmg_chebyshev_estimate(pmg_chebyshev *s);
 /* fused smoother: u <- smooth(u, rhs); zero_guess => u is taken as 0 on entry.  tmp: work vector.
    On return *result points at the vector that holds the smoothed iterate (u or tmp). */
 int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp,
                          int zero_guess, pmg_vector **result);
+int pmg_chebyshev_smooth_chain(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp, int zero_guess,
+                               pmg_vector **result, int chain_in, int want_out, int *pushed_out);
 
 #ifdef __cplusplus
 }

@@ -136,6 +136,37 @@ int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const doubl
   return pmgk_apply(&op->lv, mode, u, b, xold, out, f1, f2, ctx->stream);
 }
 
+/* Can a chain of applies on this operator exchange its ghost planes by fused pushes?  (slab with neighbours, the level's
+   kernel supports it, both ping-pong vectors mapped on the neighbours; identical answer on every rank: slabs are equal and
+   vectors are created collectively) */
+int pmg_apply_chain_ok(const pmg_operator *op, int mode, double *v0, double *v1)
+{
+  pmg_context *ctx = op->ctx;
+  pmgk_push d;
+  if (!op->lay.active || !ctx->has_comm || op->lay.gathered || ctx->overlap) return 0;
+  if (!pmgk_apply_can_push(&op->lv, mode)) return 0;
+  return pmg_p2p_push_desc(ctx, &op->lay, v0, &d) && pmg_p2p_push_desc(ctx, &op->lay, v1, &d);
+}
+
+/* One apply of a chain (pmg_apply_chain_ok): consume = u was written by the previous apply of the chain, which pushed its
+   boundary planes into the neighbours' ghost planes, so no exchange happens here; push = the next apply of the chain reads
+   `out`.  Reference: src.update_ghost_values() before every cell loop (:661) -- here the cell loop of the previous step
+   has already delivered them. */
+int pmg_apply_chained(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1,
+                      double f2, int consume, int push)
+{
+  PMG_CHECK(pmg_enter(op->ctx));
+  pmg_context *ctx = op->ctx;
+  if (!op->lay.active) return PMG_OK;
+  pmgk_push d;
+  if (push) { if (!pmg_p2p_push_desc(ctx, &op->lay, out, &d)) return PMG_ERR_ARG; }
+  else if (!pmg_p2p_push_desc(ctx, &op->lay, u, &d)) return PMG_ERR_ARG; /* consume only: the flag words, no target */
+  d.push = push; d.consume = consume;
+  if (!consume) PMG_CHECK(pmg_halo_update(ctx, &op->lay, u));
+  else ++ctx->p2p.n_fused;
+  return pmgk_apply_push(&op->lv, mode, u, b, xold, out, f1, f2, &d, ctx->stream);
+}
+
 static int apply_mode(const pmg_operator *op, int mode, pmg_vector *dst, const pmg_vector *src, const pmg_vector *b,
                       const pmg_vector *xold, double f1, double f2)
 {

@@ -72,11 +72,15 @@ int pmg_p2p_init(pmg_context *ctx)
   /* opt-in (PMG_P2P_HALO=1).  Measured on 2 B200s (profiles/r02_halo_p2p_2gpu.txt, C2 per GPU): V-cycle 7.05 ms with the push
      kernel against 6.76 ms with the NCCL group -- two flag round trips + the launch cost as much as NCCL's protocol, and neither
      overlaps with the apply.  Kept as the base of a push fused into the apply kernel's epilogue. */
-  const char *env = getenv("PMG_P2P_HALO");
-  const int wanted = (env && atoi(env) != 0);
+  const char *env = getenv("PMG_P2P_HALO"), *envf = getenv("PMG_FUSED_HALO");
+  const int explicit_push = (env && atoi(env) != 0);
+  /* The fused push (the smoother's applies store their boundary planes into the neighbours' ghost planes themselves,
+     csrc/pmg_apply_plane_launch.h) is on by default: it removes the exchange between two Chebyshev steps altogether. */
+  const int fused = !(envf && atoi(envf) == 0);
+  const int wanted = explicit_push || fused;
   PMG_CUDA(cudaMalloc(&pp->msg_dev, 3 * P2P_MSG_BYTES));
-  PMG_CUDA(cudaMalloc((void **)&pp->mailbox, 8 * sizeof(uint64_t)));
-  PMG_CUDA(cudaMemset(pp->mailbox, 0, 8 * sizeof(uint64_t)));
+  PMG_CUDA(cudaMalloc((void **)&pp->mailbox, 16 * sizeof(uint64_t)));
+  PMG_CUDA(cudaMemset(pp->mailbox, 0, 16 * sizeof(uint64_t)));
   p2p_msg mine, lo, up;
   memset(&mine, 0, sizeof(mine));
   mine.ok = wanted && cudaIpcGetMemHandle(&mine.handle, pp->mailbox) == cudaSuccess;
@@ -92,6 +96,8 @@ int pmg_p2p_init(pmg_context *ctx)
   int all = 0;
   PMG_CHECK(all_ranks_agree(ctx, ok, &all));
   pp->enabled = all;
+  pp->explicit_push = all && explicit_push;
+  pp->fused = all && fused;
   return PMG_OK;
 }
 
@@ -186,7 +192,7 @@ int pmg_p2p_halo(pmg_context *ctx, const pmg_layout *lay, double *d, cudaStream_
 {
   pmg_p2p *pp = &ctx->p2p;
   *done = 0;
-  if (!pp->enabled) return PMG_OK;
+  if (!pp->enabled || !pp->explicit_push) return PMG_OK;
   for (int i = 0; i < pp->n_reg; ++i)
     if (pp->reg[i].base == d) {
       const pmg_p2p_reg *r = &pp->reg[i];
@@ -207,4 +213,23 @@ int pmg_p2p_halo(pmg_context *ctx, const pmg_layout *lay, double *d, cudaStream_
       return PMG_OK;
     }
   return PMG_OK;
+}
+
+int pmg_p2p_push_desc(pmg_context *ctx, const pmg_layout *lay, double *out, pmgk_push *desc)
+{
+  pmg_p2p *pp = &ctx->p2p;
+  memset(desc, 0, sizeof(*desc));
+  if (!pp->enabled || !pp->fused || lay->gathered || !lay->active) return 0;
+  for (int i = 0; i < pp->n_reg; ++i)
+    if (pp->reg[i].base == out) {
+      const pmg_p2p_reg *r = &pp->reg[i];
+      desc->out_lower = lay->lower >= 0 ? (double *)r->peer_lower : NULL;
+      desc->out_upper = lay->upper >= 0 ? (double *)r->peer_upper : NULL;
+      desc->lower_z0 = r->lower_z0; desc->upper_z0 = r->upper_z0;
+      desc->mailbox = pp->mailbox;
+      desc->mailbox_lower = lay->lower >= 0 ? pp->mb_lower : NULL;
+      desc->mailbox_upper = lay->upper >= 0 ? pp->mb_upper : NULL;
+      return 1;
+    }
+  return 0;
 }

@@ -222,6 +222,16 @@ int pmg_chebyshev_info(pmg_chebyshev *s, double *lambda_min, double *lambda_max,
 int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp, int zero_guess,
                          pmg_vector **result)
 {
+  return pmg_chebyshev_smooth_chain(s, u, rhs, tmp, zero_guess, result, 0, 0, NULL);
+}
+
+/* smooth() as a link of a longer chain of applies (the V-cycle: smooth, smooth, residual): chain_in = u's ghost planes were
+   pushed by the caller's previous fused apply (the first apply here consumes them, no exchange); want_out = the caller's next
+   operation is a fused apply that reads the result (the last apply here pushes too); *pushed_out = it did. */
+int pmg_chebyshev_smooth_chain(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs, pmg_vector *tmp, int zero_guess,
+                               pmg_vector **result, int chain_in, int want_out, int *pushed_out)
+{
+  if (pushed_out) *pushed_out = 0;
   if (s && s->op) PMG_CHECK(pmg_enter(s->op->ctx));
   if (!s->initialized) PMG_CHECK(pmg_chebyshev_estimate(s));
   pmg_operator *op = s->op;
@@ -231,11 +241,25 @@ int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs,
   const double theta = s->theta, delta = s->delta;
   pmg_vector *cur = u, *other = tmp;
   int other_is_xold = 0; /* does `other` hold the previous iterate? */
+  /* Slabs with neighbours: the applies of one smooth() form a chain u -> tmp -> u -> ...; each pushes the boundary planes
+     of its result into the neighbours' ghost planes from its own epilogue (one fused compute + exchange kernel), so only the
+     first apply is preceded by an exchange.  n_applies: the fused passes of this call. */
+  const int chained = pmg_apply_chain_ok(op, PMGK_CHEB_STEP, u->d, tmp->d);
+  const int n_steps = (s->degree >= 2 && fabs(delta) >= 1e-40) ? s->degree - 1 : 0;
+  const int n_applies = n_steps + (zero_guess ? 0 : 1);
+  int i_apply = 0;
+#define PMG_SMOOTH_APPLY(mode, xold_, f1_, f2_)                                                                                   \
+  do {                                                                                                                            \
+    if (chained) PMG_CHECK(pmg_apply_chained(op, mode, cur->d, rhs->d, xold_, other->d, f1_, f2_, i_apply > 0 || chain_in,        \
+                                             i_apply + 1 < n_applies || want_out));                                               \
+    else PMG_CHECK(pmg_apply_with_halo(op, mode, cur->d, rhs->d, xold_, other->d, f1_, f2_));                                    \
+    ++i_apply;                                                                                                                    \
+  } while (0)
   /* step 0: x1 = x0 + theta^-1 Dinv (rhs - A x0) */
   if (zero_guess) {
     PMG_CHECK(pmgk_scale_dinv(&op->lv, 1.0 / theta, rhs->d, cur->d, ctx->stream)); /* x1 in cur, x0 = 0 */
   } else {
-    PMG_CHECK(pmg_apply_with_halo(op, PMGK_CHEB_FIRST, cur->d, rhs->d, NULL, other->d, 0.0, 1.0 / theta));
+    PMG_SMOOTH_APPLY(PMGK_CHEB_FIRST, NULL, 0.0, 1.0 / theta);
     pmg_vector *t = cur; cur = other; other = t; /* cur = x1, other = x0 */
     other_is_xold = 1;
   }
@@ -247,11 +271,13 @@ int pmg_chebyshev_smooth(pmg_chebyshev *s, pmg_vector *u, const pmg_vector *rhs,
       const double factor1 = rhokp * rhok, factor2 = 2.0 * rhokp / delta;
       rhok = rhokp;
       /* x_{k+2} = x_{k+1} + f1 (x_{k+1} - x_k) + f2 Dinv (rhs - A x_{k+1}), written over x_k */
-      PMG_CHECK(pmg_apply_with_halo(op, PMGK_CHEB_STEP, cur->d, rhs->d, other_is_xold ? other->d : NULL, other->d, factor1, factor2));
+      PMG_SMOOTH_APPLY(PMGK_CHEB_STEP, other_is_xold ? other->d : NULL, factor1, factor2);
       pmg_vector *t = cur; cur = other; other = t;
       other_is_xold = 1;
     }
   }
+#undef PMG_SMOOTH_APPLY
+  if (pushed_out) *pushed_out = chained && want_out && n_applies > 0;
   *result = cur;
   return PMG_OK;
 }

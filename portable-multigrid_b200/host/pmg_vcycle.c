@@ -195,14 +195,19 @@ static int v_cycle(pmg_vcycle *v, int level, pmg_vector *u, const pmg_vector *rh
   /* pre-smoothing (:157-160) */
   PMG_CHECK(mark(v, level, CAT_SMOOTH));
   int zg = zero_guess;
+  /* Slabs with neighbours: smooth, smooth, residual are one chain of applies, each reading what the one before wrote; every
+     apply pushes its boundary planes into the neighbours' ghost planes itself (fused compute + exchange), so the chain needs
+     ONE ghost exchange, before its first apply (pmg_smoother.c, pmg_operator.c: pmg_apply_chained) */
+  int pushed = 0;
   for (int s = 0; s < v->pre; ++s) {
-    PMG_CHECK(pmg_chebyshev_smooth(v->sm[level], cur, rhs, other, zg, &r));
+    PMG_CHECK(pmg_chebyshev_smooth_chain(v->sm[level], cur, rhs, other, zg, &r, pushed, 1, &pushed));
     if (r != cur) { other = cur; cur = r; }
     zg = 0;
   }
   /* residual = src - A dst (:163-166), restricted to the next coarser level (:169-172) */
   PMG_CHECK(mark(v, level, CAT_OTHER));
   if (zg) PMG_CHECK(pmg_vector_copy(v->res[level], rhs)); /* no pre-smoothing and u = 0: residual = rhs */
+  else if (pushed) PMG_CHECK(pmg_apply_chained(v->op[level], PMGK_RESIDUAL, cur->d, rhs->d, NULL, v->res[level]->d, 0.0, 0.0, 1, 0));
   else PMG_CHECK(pmg_laplace_operator_residual(v->op[level], v->res[level], rhs, cur));
   PMG_CHECK(mark(v, level, CAT_TRANSFER));
   PMG_CHECK(pmg_vector_set(v->rhs[level - 1], 0.0));
@@ -215,8 +220,9 @@ static int v_cycle(pmg_vcycle *v, int level, pmg_vector *u, const pmg_vector *rh
   PMG_CHECK(pmg_transfer_prolongate_and_add(v->tr[level], cur, v->sol[level - 1]));
   /* post-smoothing (:185-188) */
   PMG_CHECK(mark(v, level, CAT_SMOOTH));
+  pushed = 0;
   for (int s = 0; s < v->post; ++s) {
-    PMG_CHECK(pmg_chebyshev_smooth(v->sm[level], cur, rhs, other, 0, &r));
+    PMG_CHECK(pmg_chebyshev_smooth_chain(v->sm[level], cur, rhs, other, 0, &r, pushed, s + 1 < v->post, &pushed));
     if (r != cur) { other = cur; cur = r; }
   }
   PMG_CHECK(mark(v, level, CAT_OTHER));

@@ -43,6 +43,8 @@ def lib():
         _lib.pmg_context_stream.argtypes = [_vp]
         _lib.pmg_context_launch_count.restype = C.c_int64
         _lib.pmg_context_launch_count.argtypes = [_vp]
+        _lib.pmg_context_fused_halo_count.restype = C.c_int64
+        _lib.pmg_context_fused_halo_count.argtypes = [_vp]
     return _lib
 
 
@@ -90,6 +92,10 @@ class Context:
 
     def launch_count(self):
         return int(lib().pmg_context_launch_count(self.h))
+
+    def fused_halo_count(self):
+        """Applies whose ghost planes came from the previous apply's fused push (no exchange of their own)."""
+        return int(lib().pmg_context_fused_halo_count(self.h))
 
     def microbench(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -20,6 +20,13 @@ struct PlaneHostExec {
 };
 
 static bool g_plane_reverse = false;
+// fused ghost push under the emulator: the neighbours' copies of `out` and their first stored planes (emu_plane_set_push)
+static double *g_push_lo = nullptr, *g_push_hi = nullptr;
+static int g_push_lo_z0 = 0, g_push_hi_z0 = 0;
+extern "C" void emu_plane_set_push(double *lower, int lower_z0, double *upper, int upper_z0)
+{
+  g_push_lo = lower; g_push_lo_z0 = lower_z0; g_push_hi = upper; g_push_hi_z0 = upper_z0;
+}
 
 template <int P, int BX, int BY, int NT, int UZ = 1, int PR = 1, int XS = 1>
 static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, int cz_lo, int cz_hi, int z_own_lo,
@@ -27,7 +34,7 @@ static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
                      const double *u, const double *b, const double *xold, double *out, double f1, double f2,
                      const double *dinv_vec, const double *dinv_tab)
 {
-  using Tile = PmgPlaneTile<P, BX, BY, NT, -1, UZ, 0, 3, 0, PR, XS>;
+  using Tile = PmgPlaneTile<P, BX, BY, NT, -1, UZ, 0, 3, 0, PR, XS, 1>; // PUSH = 1: the emulator also covers the fused ghost push
   PmgSweepParams<P> p;
   std::memset(&p, 0, sizeof(p));
   p.nx = nx; p.ny = ny; p.nz = nz;
@@ -37,6 +44,11 @@ static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
   pmg_sweep_fill_matrices<P>(p, M, K, h);
   p.mode = mode; p.u = u; p.b = b; p.xold = xold; p.out = out; p.f1 = f1; p.f2 = f2;
   p.dinv_vec = dinv_vec; p.dinv_tab = dinv_tab;
+  { // as the launcher does (csrc/pmg_apply_plane_launch.h): pointers indexed like `out`
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    if (g_push_lo) p.push_lo = g_push_lo + plane * (z0 - g_push_lo_z0);
+    if (g_push_hi) p.push_hi = g_push_hi + plane * (z0 - g_push_hi_z0);
+  }
   p.tiles_x = Tile::tiles_of(nx, faces >> 1 & 1u, BX);
   p.tiles_y = Tile::tiles_of(ny, faces >> 3 & 1u, BY);
   const int layers = cz_hi - cz_lo;

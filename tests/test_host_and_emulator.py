@@ -213,6 +213,40 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
     assert rel_l2(got, ref) < 1e-13
 
 
+@pytest.mark.parametrize("p,small", [(1, 1), (2, 0), (3, 1), (4, 0), (4, 3), (6, 1)])
+@pytest.mark.parametrize("mode", [0, 3])
+def test_emulated_fused_ghost_push(p, small, mode, emu, oracle):
+    """Fused ghost push of the plane-per-step kernel (csrc/pmg_apply_plane.h epilogue): every rank's launch stores its
+    boundary planes of the result into the neighbours' arrays, so that afterwards each rank's ghost planes of `out` hold what
+    an exchange would have delivered -- and nothing else is written there."""
+    n = (3, 4, 6)
+    splits = [(0, 2), (2, 4), (4, 6)]
+    mf = oracle.MatrixFree(3, p, n)
+    u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (7, 8, 9))
+    Au = mf.vmult(u)
+    f1, f2 = 0.3, 0.6
+    ref = Au if mode == 0 else u + f1 * (u - xo) + f2 * mf.compute_diagonal() * (b - Au)
+    plane = mf.nd[0] * mf.nd[1]
+    slabs = [slab_of(p, n, lo, hi) for lo, hi in splits]
+    outs = [np.full(sl[1] * plane, np.nan) for sl in slabs]
+    emu.emu_plane_set_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    emu.emu_plane_set_push.restype = None
+    try:
+        for r, sl in enumerate(slabs):
+            z0, nzl = sl[0], sl[1]
+            lo = outs[r - 1].ctypes.data if r > 0 else None
+            hi = outs[r + 1].ctypes.data if r + 1 < len(slabs) else None
+            emu.emu_plane_set_push(lo, slabs[r - 1][0] if r > 0 else 0, hi, slabs[r + 1][0] if r + 1 < len(slabs) else 0)
+            cut = lambda v: v[z0 * plane:(z0 + nzl) * plane].copy()
+            emu_apply(emu, p, n, cut(u), mode=mode, b=cut(b), xold=cut(xo), f1=f1, f2=f2, small=small, chunks=2, slab=sl, out=outs[r], kernel="plane")
+    finally:
+        emu.emu_plane_set_push(None, 0, None, 0)
+    for r, sl in enumerate(slabs):  # every stored plane of every rank now equals the serial result: owned and ghost planes
+        z0, nzl = sl[0], sl[1]
+        assert not np.isnan(outs[r]).any()
+        assert rel_l2(outs[r], ref[z0 * plane:(z0 + nzl) * plane]) < 1e-13
+
+
 @pytest.mark.parametrize("p", range(1, 9))
 @pytest.mark.parametrize("small,chunks", [(2, 2), (3, 1), (3, 3), (4, 1), (4, 2)])
 def test_emulated_plane_kernel_variants(p, small, chunks, emu, oracle):

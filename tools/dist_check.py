@@ -122,6 +122,7 @@ def main():
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
+        print("applies with fused ghost push (no exchange of their own): %d, kernel launches: %d" % (ctx.fused_halo_count(), ctx.launch_count()), flush=True)
         print("DIST CHECK", "PASSED" if t.item() == 1.0 else "FAILED", "on", world, "GPUs", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if t.item() == 1.0 else 1)
