@@ -364,6 +364,18 @@ def main():
         e2e = {"value": n_dofs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_own * 8), "d2h_bytes_per_step": int(n_own * 8),
                "ms_per_step": dt * 1e3, "note": "per rank: its owned slab, pinned host buffers"}
     clocks = sampler.stop() if rank == 0 else None
+    # one eager V-cycle with event marks between its phases: device ms per level on this rank (smoother / transfer / ghost
+    # exchange / residual + copies) -- the breakdown BASELINE configs[4] asks for; outside every timed region
+    per_level = None
+    try:
+        f0 = ctx.fused_halo_count()
+        prof = mg.profile(z, r)
+        per_level = {"columns": ["smoother", "transfer", "ghost_exchange", "residual_and_copies"],
+                     "ms": [[round(float(x), 4) for x in row] for row in prof],
+                     "applies_without_exchange": int(ctx.fused_halo_count() - f0),
+                     "note": "rank 0, eager launches (the timed cycles replay a CUDA graph); row l = level l of config.levels"}
+    except Exception as e:  # never fatal for the bench line
+        per_level = {"error": str(e)}
 
     peak, peak_src = measured_peaks()
     n_local = n_dofs / world
@@ -437,7 +449,7 @@ def main():
         "apply_c3": apply_c3, "apply_c3_sweep": apply_c3_sweep,
         "cg_solve": cg,
         "e2e": e2e, "gpu_launches": int(launches_per_cycle * args.steps), "launches_per_cycle": int(launches_per_cycle),
-        "clocks": clocks,
+        "clocks": clocks, "per_level_ms": per_level,
         "roofline": {"kernel": ("pmg_var_kernel<%d>" if coefficient else "pmg_plane_kernel<%d>" if p <= 6 else "pmg_sweep_kernel<%d>") % p + " (fused Chebyshev step, finest level)",
                      "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic() if args.config == "c2" and world == 1 else None,

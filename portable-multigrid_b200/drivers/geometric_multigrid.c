@@ -5,18 +5,26 @@
  * (:267-285, :342-343), CG to 1e-12 ||b|| (:345-352).  Prints the reference's lines (:189-199, :354-355, :395).
  * Flags: --degree D (only that degree), --max-degree M (default 7), --cycles C (default 6),
  *        --cheb-degree K (default 5; BASELINE config 1 uses 3), --pre/--post (default 2).
- *        --coefficient 1, --tol T, --profile 1: see driver_common.h; --dim 2 runs the unit square (reference: dim = 3, :470).
+ *        --cells N (one run on N^dim cells, e.g. BASELINE config 4), --coefficient 1, --tol T, --profile 1: see driver_common.h; --dim 2 runs the unit square (reference: dim = 3, :470).
  */
 #include "driver_common.h"
+
+static int g_cells = 0; /* --cells N: one run on an N^dim mesh, coarsened by halving while N stays even (BASELINE config 4: N = 160 per GPU) */
 
 static int run_degree(pmg_context *ctx, int degree, int cycles, int pre, int post, int cheb)
 {
   RPRINT("============== fe_degree = %d ============== \n\n", degree);
-  for (int cycle = 0; cycle < cycles; ++cycle) {
+  for (int cycle = 0; cycle < (g_cells > 0 ? 1 : cycles); ++cycle) {
     RPRINT("\n\nCycle %d\n", cycle);
     level_t lv[MAXL];
-    const int L = cycle + 1; /* create_geometric_coarsening_sequence: 1, 2, 4, ... cells per direction */
+    int L = cycle + 1; /* create_geometric_coarsening_sequence: 1, 2, 4, ... cells per direction */
     for (int l = 0; l < L; ++l) { lv[l].degree = degree; lv[l].n = 1 << l; }
+    if (g_cells > 0) {
+      int cells[MAXL], nc = 0;
+      for (int m = g_cells; ; m /= 2) { cells[nc++] = m; if (m % 2 || m == 1) break; }
+      L = nc;
+      for (int l = 0; l < L; ++l) { lv[l].degree = degree; lv[l].n = cells[nc - 1 - l]; }
+    }
     RPRINT(" Number of degrees of freedom: %lld (by level: ", n_dofs_of(degree, lv[L - 1].n));
     for (int l = 0; l < L; ++l) RPRINT("%lld%s", n_dofs_of(degree, lv[l].n), l == L - 1 ? ")" : ", ");
     RPRINT("\n");
@@ -35,6 +43,7 @@ int main(int argc, char **argv)
   const int pre = arg_int(argc, argv, "--pre", 2), post = arg_int(argc, argv, "--post", 2);
   common_options(argc, argv);
   g_dim = arg_int(argc, argv, "--dim", 3);
+  g_cells = arg_int(argc, argv, "--cells", 0);
   pmg_context *ctx;
   CK(driver_make_context(&ctx, arg_int(argc, argv, "--device", 0)));
   for (int d = (only ? only : 1); d <= (only ? only : max_degree); ++d)
