@@ -112,13 +112,23 @@ int pmg_dim2_apply(const pmgk_level *lv, int mode, const double *u, const double
 int pmg_var_dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold, double *out,
                      double f1, double f2, cudaStream_t s, int *geom);
 
+/* Small coarse levels run the cell-tile kernel (direct loads, lowest launch-to-result latency on one GPU) -- unless the level is
+   a slab with neighbours: there every apply of the cell-tile kernel costs a ghost exchange (~17-30 us), which the plane-per-step
+   kernel delivers from its own epilogue (fused push), so distributed levels of degrees 1..6 with >= 2 cell layers take it. */
+static bool small_level_of(const pmgk_level *lv)
+{
+  const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
+  const bool small = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
+  const bool slab_with_neighbours = lv->z_own_lo > 0 || lv->z_own_hi < lv->Nz;
+  return small && !(slab_with_neighbours && lv->cz_hi - lv->cz_lo >= 2);
+}
+
 static int dispatch(const pmgk_level *lv, int mode, const double *u, const double *b, const double *xold,
                     double *out, double f1, double f2, cudaStream_t s, int *geom, int part = PMGK_PART_ALL)
 {
-  const int64_t n_loc = (int64_t)lv->Nx * lv->Ny * lv->nzl;
   /* the plane-per-step and the line-marching kernel launch in parts (their launches are cut into z-chunks) */
   const bool chunked_kernel = lv->dim == 3 && !lv->coef &&
-                              (lv->tile_variant == 1 || lv->tile_variant == 6 || (lv->tile_variant == 0 && !(n_loc < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5)));
+                              (lv->tile_variant == 1 || lv->tile_variant == 6 || (lv->tile_variant == 0 && !small_level_of(lv)));
   if (part != PMGK_PART_ALL && !chunked_kernel) return PMG_ERR_UNSUPPORTED;
   if (lv->dim == 2) return pmg_dim2_apply(lv, mode, u, b, xold, out, f1, f2, s, geom);
   if (lv->nz < 1 || lv->cz_hi <= lv->cz_lo) return PMG_ERR_ARG;
@@ -128,8 +138,7 @@ static int dispatch(const pmgk_level *lv, int mode, const double *u, const doubl
      measured on B200 (tools/small_levels.py) 5.6-7.2 us against 7.0-12.3 us per fused step for Q1 up to 32^3 cells and
      12.3 against 16.4 us for Q2 on 32^3; from 64^3 cells on the line-marching kernel wins (14.3 : 17.1, 38.9 : 55.3 us).
      1 = line-marching always; 2, 3 = cell-tile always (small / large tiles); 6 = plane-per-step kernel always. */
-  const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
-  const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
+  const bool small_level = small_level_of(lv);
   /* round 2: the plane-per-step kernel (csrc/pmg_apply_plane.h) takes the large levels of degrees 1..6 (measured at 100 M DoFs,
      apply / fused step in GDoF/s against the line-marching kernel: Q2 170 / 123 : 112 / 80, Q4 140 / 98 : 122 / 87);
      tile_variant 6 forces it, 1 forces the line-marching kernel */
@@ -200,8 +209,7 @@ thread_local const pmgk_push *pmg_tl_push = nullptr;
 
 static bool plane_kernel_level(const pmgk_level *lv)
 {
-  const int64_t n_local = (int64_t)lv->Nx * lv->Ny * lv->nzl;
-  const bool small_level = n_local < (lv->degree == 1 ? 100000 : 300000) && lv->degree <= 5;
+  const bool small_level = small_level_of(lv);
   return lv->dim == 3 && !lv->coef && lv->degree <= PMG_PLANE_MAX_DEGREE && (lv->tile_variant == 6 || (lv->tile_variant == 0 && !small_level));
 }
 

@@ -88,6 +88,11 @@ PMG_HD void pmg_plane_stg(double *ptr, double v)
 #endif
 }
 
+// Flag words of the fused ghost exchange in a rank's mailbox (csrc/pmg_apply_plane_launch.h; words 0..5 belong to the stand-alone
+// push kernel, csrc/pmg_halo.cu).  FROM_LO / FROM_HI are written by the lower / upper neighbour: the number of fused launches
+// whose chunks at the slab end that faces me they have completed; EPOCH_LO / EPOCH_HI are my own counts for my two slab ends.
+enum { PMG_FUSED_FROM_LO = 8, PMG_FUSED_FROM_HI = 9, PMG_FUSED_EPOCH_LO = 10, PMG_FUSED_EPOCH_HI = 11, PMG_FUSED_TICKET_LO = 12, PMG_FUSED_TICKET_HI = 13 };
+
 // P: degree; BX x BY: cells per CTA; NT_: threads; FM: epilogue mode the kernel is compiled for (-1: p.mode);
 // UZ: 1 = the P steps of a cell layer are unrolled (z matrices as immediate constants), 0 = rolled (z matrices indexed)
 // LW_: lanes per u row in the loader (>= the row length BX P + P + 1, divides NT_; 0 = smallest such number): a thread loads
@@ -647,6 +652,10 @@ struct PmgPlaneTile {
         pl.n = (q >= mc.q_lo && q < mc.q_hi) ? 1 : 0; pl.q[0] = q; pl.q[1] = 0; pl.os[1] = 0;
         pl.os[0] = (P == 1) ? ((L - 1) & 1) : (jz == 0) ? P - 1 + ((L - 1) & 1) : jz - 1;
       }
+      // fused ghost exchange: the slab's upper ghost plane is about to be fetched -- only now does this CTA need the upper
+      // neighbour's word that it has pushed it (and has stopped reading the ghost planes this CTA's last epilogues push into)
+      if constexpr (PUSH != 0)
+        if (fetch && gz + ND == p.z_own_hi && (p.consume & 1) && p.mb_hi) ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI);
       ex.for_each_thread([&](int, ThreadState &st) {
         load_plane(p, st, t.plane, smem, mc.base32, fs, fetch);
         if (pl.n > 0 && !drain) epi_issue(p, t, st, pl.q[0], mc.eq);
@@ -702,6 +711,9 @@ struct PmgPlaneTile {
     mc.eq = (int64_t)(gz_first - P - 1 - p.z0) * t.plane + t.tile0;
     const double *up = p.u + (int64_t)(gz_first - p.z0) * t.plane;
 
+    // (a march so short that its first fetches already reach the upper ghost plane waits for the neighbour up front)
+    if constexpr (PUSH != 0)
+      if (gz_first + ND > p.z_own_hi && mc.gz_last >= p.z_own_hi && (p.consume & 1) && p.mb_hi) ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI);
     ex.for_each_thread([&](int tid, ThreadState &st) { decode(p, t, tid, st, smem); st.ld_src = up + st.ld_off; });
     ex.sync();
     ex.for_each_thread([&](int, ThreadState &st) {

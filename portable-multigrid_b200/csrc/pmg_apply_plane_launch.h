@@ -7,15 +7,6 @@
 
 namespace {
 
-template <class Tile>
-struct PmgPlaneDeviceExec {
-  typename Tile::ThreadState st;
-  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-
-// flag words of the fused ghost exchange in a rank's mailbox (words 0..5 belong to the stand-alone push kernel, csrc/pmg_halo.cu)
-enum { PMG_FUSED_FROM_LO = 8, PMG_FUSED_FROM_HI = 9, PMG_FUSED_EPOCH = 10, PMG_FUSED_TICKET = 11 };
 __device__ __forceinline__ void pmg_st_release_sys(unsigned long long *p, unsigned long long v)
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
@@ -26,6 +17,22 @@ __device__ __forceinline__ unsigned long long pmg_ld_acquire_sys(const unsigned 
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+
+template <class Tile>
+struct PmgPlaneDeviceExec {
+  typename Tile::ThreadState st;
+  template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  // block until *flag >= *epoch (system scope: the flag is written by a neighbour GPU over NVLink)
+  __device__ __forceinline__ void wait_flag(const unsigned long long *flag, const unsigned long long *epoch)
+  {
+    if (threadIdx.x == 0) {
+      const unsigned long long e = pmg_ld_acquire_sys(epoch);
+      while (pmg_ld_acquire_sys(flag) < e) { }
+    }
+    __syncthreads();
+  }
+};
 
 template <int P, int BX, int BY, int NT, int MINB, int UZ, int FM, int PR, int XS, int PUSH>
 __global__ void __launch_bounds__(NT, MINB)
@@ -42,40 +49,42 @@ pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, i
   const int group = b / (p.tiles_x * p.tiles_y);
   int chunk = chunk_first + group * chunk_stride;
   // ---- fused ghost exchange (p.mb: whole launches of slabs with neighbours) ---------------------------------------------
-  // The chunks that touch the slab's ends go FIRST (groups 0 and 1), the others after them: the boundary planes are on their
-  // way over NVLink while the bulk of the launch computes, and by the time the neighbours' next launch needs them they have
-  // long arrived.  Flag words (PMG_FUSED_*): the neighbours write FROM_LO / FROM_HI of my mailbox = the number of fused
-  // launches whose boundary chunks they have completed; EPOCH = my own count.  All ranks issue the same launches.
-  bool boundary = false;
+  // Launch order of the chunks: the one at the slab's TOP first, the one at its BOTTOM last.  The top chunk pushes the slab's
+  // last p planes at the end of its march -- early in the launch -- and the upper neighbour's bottom chunk, which needs them at
+  // the start of ITS march, runs last in the next launch: the flag has long arrived.  The bottom chunk pushes plane z_own_lo at
+  // the start of its march, late in the launch; the lower neighbour's top chunk needs it for the LAST plane of its march
+  // (ex.wait_flag in Tile::layer), a whole chunk march later.  Nobody spins in the steady state, interior chunks never look at
+  // a flag.  Flag words: PMG_FUSED_* (csrc/pmg_apply_plane.h); every rank issues the same sequence of fused launches.
+  bool at_lo = false, at_hi = false;
   if (PUSH && p.mb) {
-    chunk = group == 0 ? 0 : group == 1 ? p.n_chunks - 1 : group - 1;
-    const bool at_lo = chunk == 0, at_hi = chunk == p.n_chunks - 1;
-    boundary = at_lo || at_hi;
-    if (boundary && p.consume) {
-      // u's ghost planes were pushed by the neighbours' previous fused launch: wait until they say it is complete.  That
-      // also tells me that they have stopped reading the ghost planes my own pushes of this launch overwrite (the vector
-      // written now was last read as u two launches ago).
-      if (threadIdx.x == 0) {
-        const unsigned long long e = pmg_ld_acquire_sys(p.mb + PMG_FUSED_EPOCH);
-        if (at_lo && p.mb_lo) while (pmg_ld_acquire_sys(p.mb + PMG_FUSED_FROM_LO) < e) { }
-        if (at_hi && p.mb_hi) while (pmg_ld_acquire_sys(p.mb + PMG_FUSED_FROM_HI) < e) { }
-      }
-      __syncthreads();
-    }
+    const int last = p.n_chunks - 1;
+    if (!(p.consume & 2)) chunk = group == 0 ? last : group == last ? 0 : group; // (bit 1: natural order, experiments)
+    at_lo = chunk == 0; at_hi = chunk == last;
+    // u's lower ghost planes were pushed by the lower neighbour's previous fused launch: wait until its top chunk is complete
+    // (which also says that it has stopped reading the ghost plane this chunk's first epilogue pushes into)
+    if (at_lo && (p.consume & 1) && p.mb_lo) ex.wait_flag(p.mb + PMG_FUSED_FROM_LO, p.mb + PMG_FUSED_EPOCH_LO);
   }
   Tile::run(p, ex, pmg_plane_smem, tile_x, tile_y, chunk);
-  if (!PUSH || !boundary) return;
-  __threadfence_system(); // this thread's peer stores are visible system-wide before its CTA takes a ticket
+  if (!PUSH || !(at_lo || at_hi)) return;
+  // the CTA's stores (peer stores included) are ordered before the ticket by the barrier + the fence of the thread that takes it
+  // (fences are cumulative: the pattern of a grid-wide barrier)
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned long long n_boundary = (unsigned long long)p.tiles_x * p.tiles_y * (p.n_chunks > 1 ? 2 : 1);
-    if (atomicAdd(p.mb + PMG_FUSED_TICKET, 1ull) == n_boundary - 1) { // the last boundary CTA: everything is fenced
-      p.mb[PMG_FUSED_TICKET] = 0;
-      const unsigned long long e = pmg_ld_acquire_sys(p.mb + PMG_FUSED_EPOCH) + 1;
+    __threadfence_system();
+    const unsigned long long tiles = (unsigned long long)p.tiles_x * p.tiles_y;
+    if (at_lo && atomicAdd(p.mb + PMG_FUSED_TICKET_LO, 1ull) == tiles - 1) { // the last CTA of the bottom chunk
+      p.mb[PMG_FUSED_TICKET_LO] = 0;
+      const unsigned long long e = pmg_ld_acquire_sys(p.mb + PMG_FUSED_EPOCH_LO) + 1;
       __threadfence_system();
       if (p.mb_lo) pmg_st_release_sys(p.mb_lo + PMG_FUSED_FROM_HI, e); // I am my lower neighbour's upper neighbour
+      pmg_st_release_sys(p.mb + PMG_FUSED_EPOCH_LO, e);
+    }
+    if (at_hi && atomicAdd(p.mb + PMG_FUSED_TICKET_HI, 1ull) == tiles - 1) { // the last CTA of the top chunk
+      p.mb[PMG_FUSED_TICKET_HI] = 0;
+      const unsigned long long e = pmg_ld_acquire_sys(p.mb + PMG_FUSED_EPOCH_HI) + 1;
+      __threadfence_system();
       if (p.mb_hi) pmg_st_release_sys(p.mb_hi + PMG_FUSED_FROM_LO, e);
-      pmg_st_release_sys(p.mb + PMG_FUSED_EPOCH, e);
+      pmg_st_release_sys(p.mb + PMG_FUSED_EPOCH_HI, e);
     }
   }
 }

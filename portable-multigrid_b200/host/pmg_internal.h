@@ -78,6 +78,7 @@ typedef struct pmg_p2p {
   int enabled;                        /* the neighbours' mailboxes (and, per vector, arrays) are mapped */
   int explicit_push;                  /* stand-alone exchanges use the push kernel instead of the NCCL group (PMG_P2P_HALO=1) */
   int fused;                          /* the smoother's applies push their boundary planes themselves (PMG_FUSED_HALO, default on) */
+  int64_t push_min_bytes;             /* stand-alone exchanges of at least this many bytes per neighbour pair use the push kernel (PMG_P2P_MIN_BYTES) */
   void *msg_dev;                      /* device scratch of the handle exchange */
   uint64_t *mailbox, *mb_lower, *mb_upper;
   pmg_p2p_reg reg[PMG_P2P_MAX_REG];

@@ -161,7 +161,12 @@ int pmg_apply_chained(const pmg_operator *op, int mode, double *u, const double 
   pmgk_push d;
   if (push) { if (!pmg_p2p_push_desc(ctx, &op->lay, out, &d)) return PMG_ERR_ARG; }
   else if (!pmg_p2p_push_desc(ctx, &op->lay, u, &d)) return PMG_ERR_ARG; /* consume only: the flag words, no target */
-  d.push = push; d.consume = consume;
+  d.push = push; d.consume = consume ? 1 : 0;
+  {
+    static int natural_order = -1; /* PMG_FUSED_ORDER=0: boundary chunks in their natural place instead of first (experiments) */
+    if (natural_order < 0) { const char *e = getenv("PMG_FUSED_ORDER"); natural_order = (e && atoi(e) == 0) ? 1 : 0; }
+    if (natural_order) d.consume |= 2;
+  }
   if (!consume) PMG_CHECK(pmg_halo_update(ctx, &op->lay, u));
   else ++ctx->p2p.n_fused;
   return pmgk_apply_push(&op->lv, mode, u, b, xold, out, f1, f2, &d, ctx->stream);

@@ -16,6 +16,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* stand-alone exchanges switch from the NCCL group to the push kernel at this size (0 = never); set from the measurement in
+   profiles/r02_halo_exchange_by_size_2gpu.txt */
+#define PMG_P2P_MIN_BYTES_DEFAULT 0
 #define P2P_MSG_BYTES 128 /* cudaIpcMemHandle_t (64 bytes) + the first stored plane of the sender's slab + a validity word */
 
 typedef struct p2p_msg {
@@ -97,6 +100,13 @@ int pmg_p2p_init(pmg_context *ctx)
   PMG_CHECK(all_ranks_agree(ctx, ok, &all));
   pp->enabled = all;
   pp->explicit_push = all && explicit_push;
+  {
+    /* large exchanges are bandwidth bound and the push kernel moves them at NVLink speed with 148 CTAs, small ones are latency
+       bound and level with NCCL (profiles/r02_halo_p2p_2gpu.txt): PMG_P2P_MIN_BYTES sets the switch-over (bytes one rank sends
+       per exchange; default: see below) */
+    const char *em = getenv("PMG_P2P_MIN_BYTES");
+    pp->push_min_bytes = em ? (int64_t)atof(em) : PMG_P2P_MIN_BYTES_DEFAULT;
+  }
   pp->fused = all && fused;
   return PMG_OK;
 }
@@ -192,7 +202,11 @@ int pmg_p2p_halo(pmg_context *ctx, const pmg_layout *lay, double *d, cudaStream_
 {
   pmg_p2p *pp = &ctx->p2p;
   *done = 0;
-  if (!pp->enabled || !pp->explicit_push) return PMG_OK;
+  if (!pp->enabled) return PMG_OK;
+  if (!pp->explicit_push) { /* by size: the same decision on every rank (equal slabs) */
+    const int64_t bytes = 8 * lay->plane * (lay->degree + 1);
+    if (pp->push_min_bytes <= 0 || bytes < pp->push_min_bytes) return PMG_OK;
+  }
   for (int i = 0; i < pp->n_reg; ++i)
     if (pp->reg[i].base == d) {
       const pmg_p2p_reg *r = &pp->reg[i];
