@@ -535,14 +535,6 @@ struct PmgPlaneTile {
     // plane bases (uniform) + 32-bit element indices (a local vector holds < 2^31 dofs)
     const double *pu = p.u + eoff + st.e_off, *pd = (MODE >= PMG_MODE_CHEB_FIRST && p.dinv_vec) ? p.dinv_vec + eoff + st.e_off : nullptr;
     double *po = p.out + eoff + st.e_off;
-    // the neighbour's copy of this plane, when it holds it as a ghost plane (fused ghost push; a slab has >= 2 cell layers,
-    // so a plane goes to at most one neighbour)
-    double *pqb = nullptr;
-    if (PUSH) {
-      if (p.push_lo && gz == p.z_own_lo) pqb = p.push_lo;
-      else if (p.push_hi && gz >= p.z_own_hi - P) pqb = p.push_hi;
-    }
-    double *pq = (PUSH && pqb) ? pqb + eoff + st.e_off : nullptr;
     PMG_OPAQUE_PTR(pu); PMG_OPAQUE_PTR(pd); PMG_OPAQUE_PTR(po);
     const int rstep = ER * p.Nx;
 #pragma unroll
@@ -557,9 +549,7 @@ struct PmgPlaneTile {
         if (NA >= 3 && has_xo) xo = st.ein[2][k];
         if (MODE >= PMG_MODE_CHEB_FIRST) dinv = pd ? pmg_plane_ldg(pd + g) : Tz[T * (st.e_ty >> (4 * k) & 0xFu)];
         const double y = Os[k * ER * OP];
-        const double val = epi_value<MODE>(p, y, uc, bb, xo, dir, dinv);
-        pmg_plane_stg(po + g, val);
-        if (PUSH && pq) pmg_plane_stg(pq + g, val);
+        pmg_plane_stg(po + g, epi_value<MODE>(p, y, uc, bb, xo, dir, dinv));
       }
     }
     if (DIR && t.xextra && tid < ERW) { // the mesh's last vertex line in x: Dirichlet dofs (identity rows), read directly
@@ -569,9 +559,7 @@ struct PmgPlaneTile {
         const double uc = pmg_plane_ldg(p.u + g);
         const double bb = (MODE != PMG_MODE_APPLY) ? pmg_plane_ldg(p.b + g) : 0.0;
         const double xo = has_xo ? pmg_plane_ldg(p.xold + g) : 0.0;
-        const double val = epi_value<MODE>(p, 0.0, uc, bb, xo, true, 1.0);
-        pmg_plane_stg(p.out + g, val);
-        if (PUSH && pqb) pmg_plane_stg(pqb + g, val);
+        pmg_plane_stg(p.out + g, epi_value<MODE>(p, 0.0, uc, bb, xo, true, 1.0));
       }
     }
   }
@@ -652,10 +640,6 @@ struct PmgPlaneTile {
         pl.n = (q >= mc.q_lo && q < mc.q_hi) ? 1 : 0; pl.q[0] = q; pl.q[1] = 0; pl.os[1] = 0;
         pl.os[0] = (P == 1) ? ((L - 1) & 1) : (jz == 0) ? P - 1 + ((L - 1) & 1) : jz - 1;
       }
-      // fused ghost exchange: the slab's upper ghost plane is about to be fetched -- only now does this CTA need the upper
-      // neighbour's word that it has pushed it (and has stopped reading the ghost planes this CTA's last epilogues push into)
-      if constexpr (PUSH != 0)
-        if (fetch && gz + ND == p.z_own_hi && (p.consume & 1) && p.mb_hi) ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI);
       ex.for_each_thread([&](int, ThreadState &st) {
         load_plane(p, st, t.plane, smem, mc.base32, fs, fetch);
         if (pl.n > 0 && !drain) epi_issue(p, t, st, pl.q[0], mc.eq);
@@ -711,9 +695,16 @@ struct PmgPlaneTile {
     mc.eq = (int64_t)(gz_first - P - 1 - p.z0) * t.plane + t.tile0;
     const double *up = p.u + (int64_t)(gz_first - p.z0) * t.plane;
 
-    // (a march so short that its first fetches already reach the upper ghost plane waits for the neighbour up front)
+    // Fused ghost exchange: the chunk that reaches the slab's upper ghost plane needs the upper neighbour's word that it has
+    // pushed it (and has stopped reading the ghost planes this CTA pushes into after its march) only before the cell layer in
+    // whose steps that plane is fetched -- the last or last but one of the march.  The wait sits between two layers, never
+    // inside the step loop (a possible barrier there keeps the compiler from scheduling loads across it).
+    int l_wait = -1; // the layer before which to wait; -1: no wait
     if constexpr (PUSH != 0)
-      if (gz_first + ND > p.z_own_hi && mc.gz_last >= p.z_own_hi && (p.consume & 1) && p.mb_hi) ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI);
+      if (mc.gz_last >= p.z_own_hi && p.z_own_hi < p.Nz && (p.consume & 1) && p.mb_hi) {
+        l_wait = (p.z_own_hi - ND) / P;
+        if (l_wait <= mc.cz_first) { ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI); l_wait = -1; }
+      }
     ex.for_each_thread([&](int tid, ThreadState &st) { decode(p, t, tid, st, smem); st.ld_src = up + st.ld_off; });
     ex.sync();
     ex.for_each_thread([&](int, ThreadState &st) {
@@ -730,10 +721,46 @@ struct PmgPlaneTile {
     // (GEN = false).  The others -- the mesh's bottom layer under a Dirichlet face, the top vertex plane and the drain steps
     // after it -- take the general path.
     for (int L = mc.cz_first; L * P <= mc.gz_stop; ++L) {
+      if constexpr (PUSH != 0)
+        if (L == l_wait) ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI);
       const bool fast = L < mc.cz_end && L * P > t.zlo && (t.zhi < 0 || L * P + P - 1 < t.zhi);
       if (fast) layer<false>(p, t, ex, smem, mc, L);
       else layer<true>(p, t, ex, smem, mc, L);
     }
+  }
+  // ---- fused ghost push: the tile's part of the slab's boundary planes, as just written to p.out, goes to the neighbours ------
+  // (called by the CTAs of the bottom / top chunk after their march, csrc/pmg_apply_plane_launch.h: the march itself carries no
+  // push code -- a first version stored from the epilogue and cost the fused modes 5-10 % in registers and instruction cache)
+  template <class Exec>
+  static PMG_HD void push_boundary(const PmgSweepParams<P> &p, Exec &ex, int tile_x, int tile_y, bool at_lo, bool at_hi)
+  {
+    const int x0 = tile_x * OX, y0 = tile_y * OY;
+    const int x1 = (tile_x == p.tiles_x - 1 || x0 + OX > p.Nx) ? p.Nx : x0 + OX; // the last tile also holds the mesh's last lines
+    const int y1 = (tile_y == p.tiles_y - 1 || y0 + OY > p.Ny) ? p.Ny : y0 + OY;
+    if (x0 >= x1 || y0 >= y1) return;
+    const int w = x1 - x0, n = w * (y1 - y0);
+    const int64_t plane = (int64_t)p.Nx * p.Ny;
+    ex.sync(); // the CTA's stores to p.out are visible to all of its threads
+    ex.for_each_thread([&](int tid, ThreadState &) {
+      if (at_lo && p.push_lo) { // plane z_own_lo: the lower neighbour's upper ghost plane
+        const int64_t base = (int64_t)(p.z_own_lo - p.z0) * plane;
+        for (int e = tid; e < n; e += NT) {
+          const int r = e / w, c = e - r * w;
+          const int64_t g = base + (int64_t)(y0 + r) * p.Nx + x0 + c;
+          p.push_lo[g] = p.out[g];
+        }
+      }
+      if (at_hi && p.push_hi) { // planes [z_own_hi - P, z_own_hi): the upper neighbour's lower ghost planes
+        for (int q = p.z_own_hi - P; q < p.z_own_hi; ++q) {
+          const int64_t base = (int64_t)(q - p.z0) * plane;
+          for (int e = tid; e < n; e += NT) {
+            const int r = e / w, c = e - r * w;
+            const int64_t g = base + (int64_t)(y0 + r) * p.Nx + x0 + c;
+            p.push_hi[g] = p.out[g];
+          }
+        }
+      }
+    });
   }
 #undef PMG_M
 #undef PMG_KX

@@ -49,16 +49,17 @@ pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, i
   const int group = b / (p.tiles_x * p.tiles_y);
   int chunk = chunk_first + group * chunk_stride;
   // ---- fused ghost exchange (p.mb: whole launches of slabs with neighbours) ---------------------------------------------
-  // Launch order of the chunks: the one at the slab's TOP first, the one at its BOTTOM last.  The top chunk pushes the slab's
-  // last p planes at the end of its march -- early in the launch -- and the upper neighbour's bottom chunk, which needs them at
-  // the start of ITS march, runs last in the next launch: the flag has long arrived.  The bottom chunk pushes plane z_own_lo at
-  // the start of its march, late in the launch; the lower neighbour's top chunk needs it for the LAST plane of its march
-  // (ex.wait_flag in Tile::layer), a whole chunk march later.  Nobody spins in the steady state, interior chunks never look at
-  // a flag.  Flag words: PMG_FUSED_* (csrc/pmg_apply_plane.h); every rank issues the same sequence of fused launches.
+  // The bottom chunk's CTAs (at_lo) need the lower neighbour's word before their march (they start in its ghost planes), the top
+  // chunk's CTAs (at_hi) only before they fetch the upper ghost plane, the last plane of their march (ex.wait_flag in
+  // Tile::layer); after the march both copy their part of the slab's boundary planes to the neighbours (Tile::push_boundary),
+  // and the last CTA of each group tells the neighbour that faces it.  Interior chunks never look at a flag.  Chunk launch
+  // order: natural (bit 1 of p.consume, the default) or top chunk first / bottom chunk last, which gives every flag at least a
+  // chunk march of slack but measured slower (host/pmg_operator.c).  Flag words: PMG_FUSED_* (csrc/pmg_apply_plane.h); every
+  // rank issues the same sequence of fused launches.
   bool at_lo = false, at_hi = false;
   if (PUSH && p.mb) {
     const int last = p.n_chunks - 1;
-    if (!(p.consume & 2)) chunk = group == 0 ? last : group == last ? 0 : group; // (bit 1: natural order, experiments)
+    if (!(p.consume & 2)) chunk = group == 0 ? last : group == last ? 0 : group;
     at_lo = chunk == 0; at_hi = chunk == last;
     // u's lower ghost planes were pushed by the lower neighbour's previous fused launch: wait until its top chunk is complete
     // (which also says that it has stopped reading the ghost plane this chunk's first epilogue pushes into)
@@ -66,11 +67,12 @@ pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, i
   }
   Tile::run(p, ex, pmg_plane_smem, tile_x, tile_y, chunk);
   if (!PUSH || !(at_lo || at_hi)) return;
+  Tile::push_boundary(p, ex, tile_x, tile_y, at_lo, at_hi);
   // the CTA's stores (peer stores included) are ordered before the ticket by the barrier + the fence of the thread that takes it
   // (fences are cumulative: the pattern of a grid-wide barrier)
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (p.consume & 8) __threadfence(); else if (!(p.consume & 4)) __threadfence_system(); // (bits 2, 3: experiments only)
     const unsigned long long tiles = (unsigned long long)p.tiles_x * p.tiles_y;
     if (at_lo && atomicAdd(p.mb + PMG_FUSED_TICKET_LO, 1ull) == tiles - 1) { // the last CTA of the bottom chunk
       p.mb[PMG_FUSED_TICKET_LO] = 0;

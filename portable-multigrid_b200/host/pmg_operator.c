@@ -112,6 +112,16 @@ static int check_vec(const pmg_operator *op, const pmg_vector *v, const char *wh
   return PMG_OK;
 }
 
+/* chunk launch order of fused launches (bit 1 of pmgk_push.consume): natural (bottom chunk first), the default -- measured
+   6.34 : 6.52 ms per C2 cycle on 2 GPUs and 7.67 : 7.92 ms on 8 against "top chunk first, bottom chunk last"
+   (PMG_FUSED_ORDER=1), which gives the flags more slack but changes the order of the memory streams */
+static int fused_order_bit(void)
+{
+  static int natural_order = -1;
+  if (natural_order < 0) { const char *e = getenv("PMG_FUSED_ORDER"); natural_order = (e && atoi(e) == 1) ? 0 : 1; }
+  return natural_order ? 2 : 0;
+}
+
 /* ghost update of u followed by the fused apply (every operator application of the path goes through here) */
 int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const double *b, const double *xold, double *out, double f1, double f2)
 {
@@ -133,6 +143,23 @@ int pmg_apply_with_halo(const pmg_operator *op, int mode, double *u, const doubl
     return pmgk_apply_part(&op->lv, mode, u, b, xold, out, f1, f2, PMGK_PART_BOUNDARY, ctx->stream);
   }
   PMG_CHECK(pmg_halo_update(ctx, &op->lay, u));
+  {
+    /* PMG_FUSED_SELFTEST=1 (experiments, one GPU): run the kernel instance that carries the fused ghost exchange -- flag words,
+       tickets, push code -- without neighbours, to time what that machinery costs by itself */
+    static int selftest = -1;
+    if (selftest < 0) { const char *e = getenv("PMG_FUSED_SELFTEST"); selftest = (e && atoi(e) != 0) ? 1 : 0; }
+    if (selftest && !ctx->has_comm && pmgk_apply_can_push(&op->lv, mode)) {
+      if (!ctx->p2p.mailbox) {
+        PMG_CUDA(cudaMalloc((void **)&ctx->p2p.mailbox, 16 * sizeof(uint64_t)));
+        PMG_CUDA(cudaMemset(ctx->p2p.mailbox, 0, 16 * sizeof(uint64_t)));
+      }
+      pmgk_push d;
+      memset(&d, 0, sizeof(d));
+      d.mailbox = ctx->p2p.mailbox; d.consume = 1 | fused_order_bit();
+      { const char *e = getenv("PMG_FUSED_SELFTEST_BITS"); if (e) d.consume |= atoi(e); }
+      return pmgk_apply_push(&op->lv, mode, u, b, xold, out, f1, f2, &d, ctx->stream);
+    }
+  }
   return pmgk_apply(&op->lv, mode, u, b, xold, out, f1, f2, ctx->stream);
 }
 
@@ -161,12 +188,7 @@ int pmg_apply_chained(const pmg_operator *op, int mode, double *u, const double 
   pmgk_push d;
   if (push) { if (!pmg_p2p_push_desc(ctx, &op->lay, out, &d)) return PMG_ERR_ARG; }
   else if (!pmg_p2p_push_desc(ctx, &op->lay, u, &d)) return PMG_ERR_ARG; /* consume only: the flag words, no target */
-  d.push = push; d.consume = consume ? 1 : 0;
-  {
-    static int natural_order = -1; /* PMG_FUSED_ORDER=0: boundary chunks in their natural place instead of first (experiments) */
-    if (natural_order < 0) { const char *e = getenv("PMG_FUSED_ORDER"); natural_order = (e && atoi(e) == 0) ? 1 : 0; }
-    if (natural_order) d.consume |= 2;
-  }
+  d.push = push; d.consume = (consume ? 1 : 0) | fused_order_bit();
   if (!consume) PMG_CHECK(pmg_halo_update(ctx, &op->lay, u));
   else ++ctx->p2p.n_fused;
   return pmgk_apply_push(&op->lv, mode, u, b, xold, out, f1, f2, &d, ctx->stream);

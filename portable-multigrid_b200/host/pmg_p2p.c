@@ -16,9 +16,10 @@
 #include <stdlib.h>
 #include <string.h>
 
-/* stand-alone exchanges switch from the NCCL group to the push kernel at this size (0 = never); set from the measurement in
-   profiles/r02_halo_exchange_by_size_2gpu.txt */
-#define PMG_P2P_MIN_BYTES_DEFAULT 0
+/* stand-alone exchanges switch from the NCCL group to the push kernel at this size (0 = never).  Measured on 8 B200s, config 5
+   (profiles/r02_driver_c5_q5_160cells_8gpu*.txt): 25 MB per exchange 0.43 ms with the NCCL group, 0.18 ms with the push kernel;
+   at 2.5 MB the two are level (profiles/r02_halo_p2p_2gpu.txt) */
+#define PMG_P2P_MIN_BYTES_DEFAULT 4000000
 #define P2P_MSG_BYTES 128 /* cudaIpcMemHandle_t (64 bytes) + the first stored plane of the sender's slab + a validity word */
 
 typedef struct p2p_msg {

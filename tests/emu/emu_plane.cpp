@@ -66,6 +66,8 @@ static void plane_go(int nx, int ny, int nz, unsigned faces, int z0, int nzl, in
         ex.reverse = g_plane_reverse;
         for (auto &v : smem) v = 1e300; // poison shared memory so stale reads show up
         Tile::run(p, ex, smem.data(), tx, ty, chunk);
+        // fused ghost push (csrc/pmg_apply_plane_launch.h): the bottom / top chunk's CTAs copy the slab's boundary planes
+        if (p.push_lo || p.push_hi) Tile::push_boundary(p, ex, tx, ty, chunk == 0, chunk == p.n_chunks - 1);
       }
 }
 
