@@ -368,6 +368,9 @@ def main():
     # exchange / residual + copies) -- the breakdown BASELINE configs[4] asks for; outside every timed region
     per_level = None
     try:
+        barrier()
+        mg.profile(z, r)  # first eager cycle after the graph replays: absorbs one-off host-side delays and rank skew
+        barrier()
         f0 = ctx.fused_halo_count()
         prof = mg.profile(z, r)
         per_level = {"columns": ["smoother", "transfer", "ghost_exchange", "residual_and_copies"],

@@ -18,8 +18,10 @@
 
 /* stand-alone exchanges switch from the NCCL group to the push kernel at this size (0 = never).  Measured on 8 B200s, config 5
    (profiles/r02_driver_c5_q5_160cells_8gpu*.txt): 25 MB per exchange 0.43 ms with the NCCL group, 0.18 ms with the push kernel;
-   at 2.5 MB the two are level (profiles/r02_halo_p2p_2gpu.txt) */
-#define PMG_P2P_MIN_BYTES_DEFAULT 4000000
+   at 2.5 MB the two are level (profiles/r02_halo_p2p_2gpu.txt), and at 6-10 MB between fused launches (config 2 on 8 GPUs) the
+   push kernel's two flag rounds cost more than they save (7.89 against 7.67 ms per cycle, and a 2.9 ms stall in the eager
+   per-level profile: profiles/r02_bench_8gpu_push_kernel_from_4MB.json) -- hence 16 MB */
+#define PMG_P2P_MIN_BYTES_DEFAULT 16000000
 #define P2P_MSG_BYTES 128 /* cudaIpcMemHandle_t (64 bytes) + the first stored plane of the sender's slab + a validity word */
 
 typedef struct p2p_msg {
