@@ -91,7 +91,8 @@ PMG_HD void pmg_plane_stg(double *ptr, double v)
 // Flag words of the fused ghost exchange in a rank's mailbox (csrc/pmg_apply_plane_launch.h; words 0..5 belong to the stand-alone
 // push kernel, csrc/pmg_halo.cu).  FROM_LO / FROM_HI are written by the lower / upper neighbour: the number of fused launches
 // whose chunks at the slab end that faces me they have completed; EPOCH_LO / EPOCH_HI are my own counts for my two slab ends.
-enum { PMG_FUSED_FROM_LO = 8, PMG_FUSED_FROM_HI = 9, PMG_FUSED_EPOCH_LO = 10, PMG_FUSED_EPOCH_HI = 11, PMG_FUSED_TICKET_LO = 12, PMG_FUSED_TICKET_HI = 13 };
+enum { PMG_FUSED_FROM_LO = 8, PMG_FUSED_FROM_HI = 9, PMG_FUSED_EPOCH_LO = 10, PMG_FUSED_EPOCH_HI = 11, PMG_FUSED_TICKET_LO = 12, PMG_FUSED_TICKET_HI = 13,
+       PMG_FUSED_ERROR = 14 /* set when a wait for a neighbour timed out */ };
 
 // P: degree; BX x BY: cells per CTA; NT_: threads; FM: epilogue mode the kernel is compiled for (-1: p.mode);
 // UZ: 1 = the P steps of a cell layer are unrolled (z matrices as immediate constants), 0 = rolled (z matrices indexed)
@@ -703,7 +704,7 @@ struct PmgPlaneTile {
     if constexpr (PUSH != 0)
       if (mc.gz_last >= p.z_own_hi && p.z_own_hi < p.Nz && (p.consume & 1) && p.mb_hi) {
         l_wait = (p.z_own_hi - ND) / P;
-        if (l_wait <= mc.cz_first) { ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI); l_wait = -1; }
+        if (l_wait <= mc.cz_first) { ex.wait_flag(p.mb, PMG_FUSED_FROM_HI, PMG_FUSED_EPOCH_HI); l_wait = -1; }
       }
     ex.for_each_thread([&](int tid, ThreadState &st) { decode(p, t, tid, st, smem); st.ld_src = up + st.ld_off; });
     ex.sync();
@@ -722,7 +723,7 @@ struct PmgPlaneTile {
     // after it -- take the general path.
     for (int L = mc.cz_first; L * P <= mc.gz_stop; ++L) {
       if constexpr (PUSH != 0)
-        if (L == l_wait) ex.wait_flag(p.mb + PMG_FUSED_FROM_HI, p.mb + PMG_FUSED_EPOCH_HI);
+        if (L == l_wait) ex.wait_flag(p.mb, PMG_FUSED_FROM_HI, PMG_FUSED_EPOCH_HI);
       const bool fast = L < mc.cz_end && L * P > t.zlo && (t.zhi < 0 || L * P + P - 1 < t.zhi);
       if (fast) layer<false>(p, t, ex, smem, mc, L);
       else layer<true>(p, t, ex, smem, mc, L);

@@ -23,12 +23,20 @@ struct PmgPlaneDeviceExec {
   typename Tile::ThreadState st;
   template <class F> __device__ __forceinline__ void for_each_thread(F f) { f((int)threadIdx.x, st); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
-  // block until *flag >= *epoch (system scope: the flag is written by a neighbour GPU over NVLink)
-  __device__ __forceinline__ void wait_flag(const unsigned long long *flag, const unsigned long long *epoch)
+  // block until mb[flag] >= mb[epoch] (system scope: the flag word is written by a neighbour GPU over NVLink).  The wait is
+  // bounded: a neighbour that never arrives (a rank that died) must not hang this GPU -- after ~4 s the CTA gives up, raises
+  // the mailbox's error word (read by pmgk_fused_error) and goes on with whatever its ghost planes hold.
+  __device__ __forceinline__ void wait_flag(unsigned long long *mb, int flag, int epoch)
   {
     if (threadIdx.x == 0) {
-      const unsigned long long e = pmg_ld_acquire_sys(epoch);
-      while (pmg_ld_acquire_sys(flag) < e) { }
+      const unsigned long long e = pmg_ld_acquire_sys(mb + epoch);
+      if (pmg_ld_acquire_sys(mb + flag) < e) {
+        const long long t0 = clock64();
+        while (pmg_ld_acquire_sys(mb + flag) < e) {
+          __nanosleep(100);
+          if (clock64() - t0 > 8000000000ll) { atomicExch(mb + PMG_FUSED_ERROR, 1ull); break; } // ~4 s at 2 GHz
+        }
+      }
     }
     __syncthreads();
   }
@@ -63,7 +71,7 @@ pmg_plane_kernel(const __grid_constant__ PmgSweepParams<P> p, int chunk_first, i
     at_lo = chunk == 0; at_hi = chunk == last;
     // u's lower ghost planes were pushed by the lower neighbour's previous fused launch: wait until its top chunk is complete
     // (which also says that it has stopped reading the ghost plane this chunk's first epilogue pushes into)
-    if (at_lo && (p.consume & 1) && p.mb_lo) ex.wait_flag(p.mb + PMG_FUSED_FROM_LO, p.mb + PMG_FUSED_EPOCH_LO);
+    if (at_lo && (p.consume & 1) && p.mb_lo) ex.wait_flag(p.mb, PMG_FUSED_FROM_LO, PMG_FUSED_EPOCH_LO);
   }
   Tile::run(p, ex, pmg_plane_smem, tile_x, tile_y, chunk);
   if (!PUSH || !(at_lo || at_hi)) return;

@@ -144,6 +144,16 @@ int pmg_sync(pmg_context *ctx)
 {
   if (!ctx) return PMG_ERR_ARG;
   PMG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->p2p.enabled && ctx->p2p.fused && ctx->p2p.mailbox) {
+    /* the fused ghost exchange bounds its waits for the neighbour GPUs (csrc/pmg_apply_plane_launch.h: ~4 s); a wait that gave
+       up left the error word set: the results since then are not to be trusted, and the caller hears about it here */
+    uint64_t err = 0;
+    PMG_CUDA(cudaMemcpy(&err, ctx->p2p.mailbox + 14 /* PMG_FUSED_ERROR */, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) {
+      pmg_set_error("fused ghost exchange: a neighbour rank did not arrive within the time limit (rank %d)", ctx->rank);
+      return PMG_ERR_CUDA;
+    }
+  }
   return PMG_OK;
 }
 

@@ -17,7 +17,7 @@ struct PlaneHostExec {
     else for (int t = 0; t < Tile::NT; ++t) f(t, st[t]);
   }
   void sync() {}
-  void wait_flag(const unsigned long long *, const unsigned long long *) {} // fused ghost exchange: no neighbour GPUs here
+  void wait_flag(unsigned long long *, int, int) {} // fused ghost exchange: no neighbour GPUs here
 };
 
 static bool g_plane_reverse = false;
