@@ -436,3 +436,30 @@ def test_emulated_coarse_cycle_matches_oracle_vcycle(p, n, faces, emu, oracle):
     out = np.full(mfs[-1].n_dofs, np.nan)
     assert emu.emu_coarse_cycle(p, L, (C.c_int * 3)(1, 1, 1), C.c_uint(faces), 2, 2, deg, theta, delta, P(out), P(r)) == 0
     assert rel_l2(out, vc.vmult(r)) < 1e-12
+
+
+def test_roofline_traffic_file_matches_the_committed_ncu_capture():
+    """bench.py reports roofline.traffic from profiles/r02_cheb_step_q4_c2.json; that number must be the dram bytes of the fused
+    Chebyshev step in the committed raw page of the ncu capture (profiles/r02_plane_q4_c2_ncu_raw.csv), not a free constant."""
+    import csv
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "r02_cheb_step_q4_c2.json")) as f:
+        j = json.load(f)
+    with open(os.path.join(root, "profiles", "r02_plane_q4_c2_ncu_raw.csv"), newline="") as f:
+        rows = list(csv.reader(f))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    seen = []
+    for r in rows[2:]:
+        if "4, 4, 4, 96, 5, 0, 3" not in r[col["Kernel Name"]]:  # the fused step: FM = 3, rolled layer loop
+            continue
+        rd = float(r[col["dram__bytes_read.sum"]].replace(",", "")) * scale[units[col["dram__bytes_read.sum"]]]
+        wr = float(r[col["dram__bytes_write.sum"]].replace(",", "")) * scale[units[col["dram__bytes_write.sum"]]]
+        seen.append(rd + wr)
+    assert seen, "the capture holds launches of the fused Chebyshev step"
+    assert min(abs(s - j["dram_bytes_per_launch"]) for s in seen) <= 1e-3 * j["dram_bytes_per_launch"]
+    assert abs(j["algorithmic_bytes_per_launch"] - 32 * 16974593) < 1
+    assert 0.9 < j["dram_bytes_per_launch"] / j["algorithmic_bytes_per_launch"] < 1.1  # no wasted re-reads
