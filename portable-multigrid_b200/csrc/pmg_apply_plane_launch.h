@@ -32,7 +32,8 @@ struct PmgPlaneDeviceExec {
       const unsigned long long e = pmg_ld_acquire_sys(mb + epoch);
       if (pmg_ld_acquire_sys(mb + flag) < e) {
         const long long t0 = clock64();
-        while (pmg_ld_acquire_sys(mb + flag) < e) {
+        // (once a wait has timed out nobody waits any more: the run is lost, it must still come to an end)
+        while (pmg_ld_acquire_sys(mb + flag) < e && pmg_ld_acquire_sys(mb + PMG_FUSED_ERROR) == 0) {
           __nanosleep(100);
           if (clock64() - t0 > 8000000000ll) { atomicExch(mb + PMG_FUSED_ERROR, 1ull); break; } // ~4 s at 2 GHz
         }
