@@ -214,14 +214,16 @@ def test_emulated_slabs_cover_the_serial_result(p, splits, kernel, emu, oracle):
 
 
 @pytest.mark.parametrize("p,small", [(1, 1), (2, 0), (3, 1), (4, 0), (4, 3), (6, 1)])
-@pytest.mark.parametrize("mode", [0, 3])
-def test_emulated_fused_ghost_push(p, small, mode, emu, oracle):
+@pytest.mark.parametrize("mode,faces", [(0, 0x3F), (3, 0x3F), (3, 0x09), (0, 0x16)])
+def test_emulated_fused_ghost_push(p, small, mode, faces, emu, oracle):
     """Fused ghost push of the plane-per-step kernel (csrc/pmg_apply_plane.h epilogue): every rank's launch stores its
     boundary planes of the result into the neighbours' arrays, so that afterwards each rank's ghost planes of `out` hold what
     an exchange would have delivered -- and nothing else is written there."""
     n = (3, 4, 6)
     splits = [(0, 2), (2, 4), (4, 6)]
-    mf = oracle.MatrixFree(3, p, n)
+    # faces: Dirichlet faces of the mesh (bits x-, x+, y-, y+, z-, z+); without a Dirichlet high face in x / y the tiles also hold
+    # the mesh's last vertex lines, which the push has to carry too
+    mf = oracle.MatrixFree(3, p, n, faces=faces)
     u, b, xo = (splitmix_src(mf.n_dofs, salt=s) for s in (7, 8, 9))
     Au = mf.vmult(u)
     f1, f2 = 0.3, 0.6
@@ -238,7 +240,8 @@ def test_emulated_fused_ghost_push(p, small, mode, emu, oracle):
             hi = outs[r + 1].ctypes.data if r + 1 < len(slabs) else None
             emu.emu_plane_set_push(lo, slabs[r - 1][0] if r > 0 else 0, hi, slabs[r + 1][0] if r + 1 < len(slabs) else 0)
             cut = lambda v: v[z0 * plane:(z0 + nzl) * plane].copy()
-            emu_apply(emu, p, n, cut(u), mode=mode, b=cut(b), xold=cut(xo), f1=f1, f2=f2, small=small, chunks=2, slab=sl, out=outs[r], kernel="plane")
+            emu_apply(emu, p, n, cut(u), mode=mode, b=cut(b), xold=cut(xo), f1=f1, f2=f2, small=small, chunks=2, slab=sl, out=outs[r], kernel="plane",
+                      faces=faces, dinv_vec=cut(mf.compute_diagonal()) if mode else None)
     finally:
         emu.emu_plane_set_push(None, 0, None, 0)
     for r, sl in enumerate(slabs):  # every stored plane of every rank now equals the serial result: owned and ghost planes
